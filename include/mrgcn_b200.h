@@ -1,0 +1,169 @@
+/* mrgcn_b200.h — C ABI of libmrgcn_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the relational graph-convolution hot path of wxwilcke/mrgcn
+ * (SURVEY.md §8b).  The reference has no FFI: its boundary is the Python nn.Module surface
+ * (mrgcn/layers/graph.py:9-11,62 ; mrgcn/models/rgcn.py:63 ; mrgcn/tasks/link_prediction.py:645).
+ * The host-side mirror in mrgcn_b200/ keeps those signatures and calls the entry points below
+ * through ctypes from a torch.autograd.Function.  Each entry point names the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless its name ends in _host
+ *   - all launches go to `stream`; no hidden synchronisation except in *_build (one-time)
+ *   - return value: 0 = ok, otherwise a cudaError_t value or MRGCN_E_* (negative);
+ *     mrgcn_last_error_string() describes the last failure of the calling thread
+ *   - caller owns every buffer (PyTorch's caching allocator on the host side)
+ *   - fp32 arithmetic, deterministic (no floating-point atomics anywhere)
+ *
+ * Edge orders of a relational graph with E stored entries, ND destination rows, NS source
+ * columns per relation block and R relation blocks (stacked adjacency A = [A_0|...|A_{R-1}],
+ * column c = r*NS + j; mrgcn/encodings/graph_structure.py:33-38):
+ *   E1  destination-major  sorted by (dst, rel, src)   rowptr[ND+1]
+ *   E2  source-major       sorted by (src, rel, dst)   colptr[NS+1]
+ *   E3  relation-major     sorted by (rel, src, dst)   relptr[R+1]
+ */
+#ifndef MRGCN_B200_H
+#define MRGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRGCN_E_BADARG   (-1)
+#define MRGCN_E_OVERFLOW (-2)
+#define MRGCN_E_NOTSUP   (-3)
+
+typedef void *mrgcn_stream_t; /* cudaStream_t */
+
+int mrgcn_version(void);
+const char *mrgcn_last_error_string(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t mrgcn_launch_count(void);
+/* Per-kernel timing for bench.py's roofline: when enabled, every kernel launch of the library is bracketed
+ * by CUDA events on its own stream.  mrgcn_profile_dump synchronises the device, writes one line per kernel
+ * name ("name launches total_ms\n") into buf (NUL terminated, truncated to cap) and clears the records;
+ * returns the number of bytes the full text needs. */
+void mrgcn_profile_enable(int on);
+int64_t mrgcn_profile_dump(char *buf, int64_t cap);
+
+/* Device view of one relational graph; every array is caller-allocated. */
+typedef struct mrgcn_graph {
+  int64_t E;
+  int32_t ND, NS, R, _pad;
+  /* E1 */
+  int32_t *rowptr;   /* [ND+1] */
+  int32_t *e1_src;   /* [E] */
+  int32_t *e1_rel;   /* [E] */
+  float   *e1_val;   /* [E] */
+  int32_t *e1_to_e2; /* [E] position of the same edge in E2 */
+  int32_t *e1_to_e3; /* [E] position of the same edge in E3 */
+  /* E2 */
+  int32_t *colptr;   /* [NS+1] */
+  int32_t *e2_src;   /* [E] */
+  int32_t *e2_dst;   /* [E] */
+  int32_t *e2_rel;   /* [E] */
+  float   *e2_val;   /* [E] */
+  /* E3 */
+  int32_t *relptr;   /* [R+1] */
+  int32_t *e3_src;   /* [E] */
+  int32_t *e3_dst;   /* [E] */
+  float   *e3_val;   /* [E] */
+  int32_t *e3_to_e2; /* [E] */
+  /* work lists (built by the host side from rowptr/colptr/relptr) */
+  int32_t *long_rows;  int32_t n_long_rows;  int32_t long_row_thresh;   /* rows with deg > thresh */
+  int32_t *long_cols;  int32_t n_long_cols;  int32_t long_col_thresh;
+  int32_t *chunk_rel;  /* [n_chunks] relation of E3 chunk c */
+  int32_t *chunk_ptr;  /* [n_chunks+1] E3 edge range of chunk c (never crosses a relation) */
+  int32_t *rel_chunk_ptr; /* [R+1] chunk range of relation r */
+  int32_t n_chunks, _pad2;
+} mrgcn_graph;
+
+/* Re-emit the reference's stacked adjacency as E1/E2/E3.
+ * Replaces: scipy CSR -> torch COO hand-off (mrgcn/data/utils.py:165-170, mrgcn/data/batch.py:144-149)
+ * and the per-call coalesce/sort inside torch.mm(sparse, dense) (mrgcn/layers/graph.py:75,95).
+ * coo_row/coo_col: int64[E] = A._indices(); coo_val: float[E] = A._values() cast exactly to fp32.
+ * ncols = A.shape[1] = R*NS.  Fills every E1/E2/E3 array of `g` (work lists are not touched).
+ * Input need not be sorted or unique (duplicates stay separate edges: a COO sums them). */
+int mrgcn_graph_build(const int64_t *coo_row, const int64_t *coo_col, const float *coo_val,
+                      int64_t E, int64_t nrows, int64_t ncols, int32_t R,
+                      mrgcn_graph *g, mrgcn_stream_t stream);
+
+/* Triples (s,p,o) -> COO of the row-normalised stacked adjacency, bit-exact with
+ * mrgcn/encodings/graph_structure.py:70-108,162-169 followed by the float32 cast of
+ * mrgcn/data/io/tarball.py:151-157: block 2p holds A[s,o]=1/outdeg_p(s), block 2p+1 the inverse,
+ * block R-1 the identity.  triples: int32[T*3] (unique), outputs sized 2T+N (include_inverse=1)
+ * or T+N.  Output order is E1 order is NOT guaranteed; feed the result to mrgcn_graph_build. */
+int mrgcn_adjacency_from_triples(const int32_t *triples, int64_t T, int32_t N, int32_t P,
+                                 int32_t include_inverse,
+                                 int64_t *coo_row, int64_t *coo_col, float *coo_val,
+                                 mrgcn_stream_t stream);
+
+/* One R-GCN layer, forward.  Replaces GraphConvolution.forward (mrgcn/layers/graph.py:62-102)
+ * plus the row-mask multiply and ReLU of RGCN._forward_full_batch (mrgcn/models/rgcn.py:78-87):
+ *
+ *   out[i,:] = act( mask[i] * ( b + sum_{e=(i,r,j)} val_e * ( M_I(r,j) + X[j,:] . W_F(r) ) ) )
+ *   M_I(r,j) = weight_I[r*NS+j,:]                       (B == 0)
+ *            = sum_b comp_I[r,b] * weight_I[b*NS+j,:]   (B  > 0, graph.py:69-72)
+ *   W_F(r)   = weight_F[r] or sum_b comp_F[r,b]*weight_F[b]      (graph.py:83-85)
+ *
+ * gI: graph of the identity term (may be NULL when weight_I is NULL);
+ * gF: graph of the feature term (may be NULL when X is NULL); they differ only in mini-batch mode
+ *     (graph.py:88-91).  Both must have the same ND.
+ * weight_I [S*NS_I, out], comp_I [R,B] or NULL, X [NS_F, in] or NULL, weight_F [S, in, out],
+ * comp_F [R,B] or NULL, bias [out] or NULL, row_mask [ND] or NULL, relu 0/1.
+ * wmix: workspace [R*in*out] (only if B>0 and X given; receives W_F(r), needed by backward)
+ * msg_I: workspace [E_I*out] (only if B>0 and weight_I given); msg_F: workspace [E_F*out]. */
+typedef struct mrgcn_layer_args {
+  const mrgcn_graph *gI, *gF;
+  int32_t in_dim, out_dim, B, relu;
+  const float *weight_I, *comp_I, *X, *weight_F, *comp_F, *bias, *row_mask;
+  float *wmix, *msg_I, *msg_F;
+  float *out; /* [ND, out] */
+} mrgcn_layer_args;
+int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);
+
+/* Backward of the same layer (replaces autograd through graph.py:62-102).
+ * gout [ND,out] = dL/d out, out = the forward result (for the ReLU mask).
+ * Gradients are written (not accumulated); NULL pointer = not wanted.
+ *   g_weight_I [S*NS_I,out]  g_comp_I [R,B]  g_weight_F [S,in,out]  g_comp_F [R,B]  g_bias [out]
+ *   g_X [NS_F,in]
+ * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term);
+ *   part [n_chunks * max(B, in*out)] ; g_wmix [R*in*out] (B>0 and feature term);
+ *   colsum_ws [ceil(ND/1024) * out]. */
+typedef struct mrgcn_layer_bwd_args {
+  mrgcn_layer_args f;     /* forward arguments (out = forward result, wmix as filled by forward) */
+  const float *gout;
+  float *g_weight_I, *g_comp_I, *g_weight_F, *g_comp_F, *g_bias, *g_X;
+  float *gact, *cbuf, *part, *g_wmix, *colsum_ws;
+} mrgcn_layer_bwd_args;
+int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_t stream);
+
+/* DistMult scorer.  Replaces score_distmult_bc (mrgcn/tasks/link_prediction.py:645-665), generic path:
+ *   score[t] = sum_k E[s_t,k] * Rel[p_t,k] * E[o_t,k]        s,p,o: int64[n] */
+int mrgcn_distmult_fwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n,
+                       const float *E, const float *Rel, int32_t h, float *score,
+                       mrgcn_stream_t stream);
+/* Backward: gE [N,h] and gRel [NR,h] are fully written (rows without triples = 0).
+ * ws: int32 workspace of mrgcn_distmult_bwd_ws_elems(n) elements. */
+int64_t mrgcn_distmult_bwd_ws_elems(int64_t n);
+int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n,
+                       const float *gscore, const float *E, const float *Rel,
+                       int64_t N, int64_t NR, int32_t h, float *gE, float *gRel, int32_t *ws,
+                       mrgcn_stream_t stream);
+
+/* Ranking.  Replaces compute_ranks_fast + filter_scores_ (link_prediction.py:557-643) for one side:
+ *   scores[f,c] = sum_k E[c,k]*Rel[p_f,k]*E[fixed_f,k]  over all candidates c in [0,N)
+ *   entries listed in filt (CSR over facts: filt_ptr[f..f+1] -> candidate ids) are set to -inf
+ *   rank[f] = #(scores[f,:] > scores[f,target_f]) + round_half_even((#ties-1)/2) + 1
+ * head=1: candidates replace the subject (fixed = object), head=0: candidates replace the object. */
+int mrgcn_distmult_rank(const int64_t *facts /* [F,3] */, int64_t F, int32_t head,
+                        const float *E, const float *Rel, int64_t N, int32_t h,
+                        const int32_t *filt_ptr, const int32_t *filt_idx, /* NULL = raw */
+                        float *scores_ws /* [F*N] workspace */, int64_t *rank, mrgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

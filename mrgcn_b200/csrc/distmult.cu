@@ -1,0 +1,235 @@
+// DistMult scorer, its backward and the ranking pass
+// (replaces /root/reference/mrgcn/tasks/link_prediction.py:645-665 score_distmult_bc,
+//  :557-573 filter_scores_ and :593-643 compute_ranks_fast).
+// Fused gather-multiply-reduce: nothing of shape (n, h) or (b, N, h) is materialised.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace mrgcn {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+
+// score[t] = sum_k (E[s,k] * Rel[p,k]) * E[o,k]      one warp per triple
+__global__ void __launch_bounds__(kThreads)
+k_distmult_fwd(const int64_t *__restrict__ s, const int64_t *__restrict__ p, const int64_t *__restrict__ o, int64_t n,
+               const float *__restrict__ E, const float *__restrict__ Rel, int h, float *__restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (t >= n) return;
+  const float *es = E + (size_t)s[t] * h, *rp = Rel + (size_t)p[t] * h, *eo = E + (size_t)o[t] * h;
+  float acc = 0.f;
+  for (int k = lane; k < h; k += 32) acc = fmaf(es[k] * rp[k], eo[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) score[t] = acc;
+}
+
+// incidence keys: entry q < n is the subject role of triple q, entry q >= n the object role of triple q-n
+__global__ void k_incidence(const int64_t *__restrict__ s, const int64_t *__restrict__ p, const int64_t *__restrict__ o,
+                            int64_t n, int32_t *__restrict__ nk, int32_t *__restrict__ nv, int32_t *__restrict__ pk,
+                            int32_t *__restrict__ pv) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  nk[t] = (int32_t)s[t]; nv[t] = (int32_t)t;
+  nk[n + t] = (int32_t)o[t]; nv[n + t] = (int32_t)(n + t);
+  pk[t] = (int32_t)p[t]; pv[t] = (int32_t)t;
+}
+
+// gE[node,:] = sum over the node's incidence run (sorted, stable => fixed order); one warp per run head
+__global__ void __launch_bounds__(kThreads)
+k_distmult_bwd_nodes(const int32_t *__restrict__ keys, const int32_t *__restrict__ vals, int64_t m, int64_t n,
+                     const int64_t *__restrict__ s, const int64_t *__restrict__ p, const int64_t *__restrict__ o,
+                     const float *__restrict__ g, const float *__restrict__ E, const float *__restrict__ Rel, int h,
+                     float *__restrict__ gE) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (q >= m) return;
+  const int node = keys[q];
+  if (q > 0 && keys[q - 1] == node) return;
+  int64_t end = q + 1;
+  while (end < m && keys[end] == node) ++end;
+  for (int k = lane; k < h; k += 32) {
+    float acc = 0.f;
+    for (int64_t x = q; x < end; ++x) {
+      const int v = vals[x];
+      const int64_t t = v < n ? v : v - n;
+      const int64_t other = v < n ? o[t] : s[t];
+      acc = fmaf(g[t], Rel[(size_t)p[t] * h + k] * E[(size_t)other * h + k], acc);
+    }
+    gE[(size_t)node * h + k] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_distmult_bwd_rels(const int32_t *__restrict__ keys, const int32_t *__restrict__ vals, int64_t n,
+                    const int64_t *__restrict__ s, const int64_t *__restrict__ o, const float *__restrict__ g,
+                    const float *__restrict__ E, int h, float *__restrict__ gRel) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (q >= n) return;
+  const int rel = keys[q];
+  if (q > 0 && keys[q - 1] == rel) return;
+  int64_t end = q + 1;
+  while (end < n && keys[end] == rel) ++end;
+  for (int k = lane; k < h; k += 32) {
+    float acc = 0.f;
+    for (int64_t x = q; x < end; ++x) {
+      const int64_t t = vals[x];
+      acc = fmaf(g[t], E[(size_t)s[t] * h + k] * E[(size_t)o[t] * h + k], acc);
+    }
+    gRel[(size_t)rel * h + k] = acc;
+  }
+}
+
+// ---- ranking -------------------------------------------------------------------------------------
+// scores[f, c] for all candidates c; one warp per (fact, candidate), the fact's fixed row and relation row
+// are staged in shared memory.  Operand order of the products follows score_distmult_bc: (s*p)*o.
+__global__ void __launch_bounds__(kThreads)
+k_rank_scores(const int64_t *__restrict__ facts, int head, const float *__restrict__ E, const float *__restrict__ Rel,
+              int64_t N, int h, float *__restrict__ scores) {
+  extern __shared__ float q[];  // [2][h]: relation row, fixed entity row
+  const int64_t f = blockIdx.y;
+  const int64_t pf = facts[3 * f + 1], fixed = head ? facts[3 * f + 2] : facts[3 * f];
+  for (int k = threadIdx.x; k < h; k += kThreads) {
+    q[k] = Rel[(size_t)pf * h + k];
+    q[h + k] = E[(size_t)fixed * h + k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * 64;
+  for (int64_t c = c0 + warp; c < min(N, c0 + 64); c += kThreads / 32) {
+    const float *ec = E + (size_t)c * h;
+    float acc = 0.f;
+    if (head) for (int k = lane; k < h; k += 32) acc = fmaf(ec[k] * q[k], q[h + k], acc);
+    else      for (int k = lane; k < h; k += 32) acc = fmaf(q[h + k] * q[k], ec[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) scores[(size_t)f * N + c] = acc;
+  }
+}
+
+__global__ void k_rank_filter(const int64_t *__restrict__ facts, int head, const int32_t *__restrict__ fptr,
+                              const int32_t *__restrict__ fidx, int64_t N, float *__restrict__ scores) {
+  const int64_t f = blockIdx.x;
+  const int64_t target = head ? facts[3 * f] : facts[3 * f + 2];
+  for (int x = fptr[f] + threadIdx.x; x < fptr[f + 1]; x += blockDim.x) {
+    int c = fidx[x];
+    if (c != target) scores[(size_t)f * N + c] = -INFINITY;   // link_prediction.py:566,572
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_rank_count(const int64_t *__restrict__ facts, int head, int64_t N, const float *__restrict__ scores,
+             int64_t *__restrict__ rank) {
+  __shared__ int gt_s[kThreads], eq_s[kThreads];
+  const int64_t f = blockIdx.x;
+  const int64_t target = head ? facts[3 * f] : facts[3 * f + 2];
+  const float *sf = scores + (size_t)f * N;
+  const float tv = sf[target];
+  int gt = 0, eq = 0;
+  for (int64_t c = threadIdx.x; c < N; c += kThreads) {
+    float v = sf[c];
+    gt += v > tv;
+    eq += v == tv;
+  }
+  gt_s[threadIdx.x] = gt; eq_s[threadIdx.x] = eq;
+  __syncthreads();
+  for (int s = kThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { gt_s[threadIdx.x] += gt_s[threadIdx.x + s]; eq_s[threadIdx.x] += eq_s[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // rank = #greater + round_half_even((#ties - 1) / 2) + 1      (link_prediction.py:632-643)
+    int64_t m = (int64_t)eq_s[0] - 1;
+    int64_t half = m / 2;
+    if (m > 0 && (m & 1) && (half & 1)) half += 1;
+    if (m < 0) half = 0;  // target itself NaN: no tie with itself; torch.round(-0.5) = -0 -> 0
+    rank[f] = gt_s[0] + half + 1;
+  }
+}
+
+static int sort_i32(int32_t *kin, int32_t *kout, int32_t *vin, int32_t *vout, int64_t m, cudaStream_t st) {
+  size_t bytes = 0;
+  MRGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, 32, st));
+  void *tmp = nullptr;
+  MRGCN_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)m, 0, 32, st);
+  cudaFreeAsync(tmp, st);
+  MRGCN_CUDA(e);
+  count_launch(3);
+  return 0;
+}
+
+}  // namespace
+}  // namespace mrgcn
+
+using namespace mrgcn;
+
+extern "C" int mrgcn_distmult_fwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n, const float *E,
+                                  const float *Rel, int32_t h, float *score, mrgcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MRGCN_REQUIRE(h > 0 && n >= 0, MRGCN_E_BADARG, "distmult_fwd: bad sizes");
+  if (n == 0) return 0;
+  MRGCN_PROF("distmult_fwd");
+  k_distmult_fwd<<<(unsigned)cdiv(n * 32, kThreads), kThreads, 0, st>>>(s, p, o, n, E, Rel, h, score);
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t mrgcn_distmult_bwd_ws_elems(int64_t n) { return 12 * (n > 0 ? n : 1); }
+
+extern "C" int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n, const float *gscore,
+                                  const float *E, const float *Rel, int64_t N, int64_t NR, int32_t h, float *gE,
+                                  float *gRel, int32_t *ws, mrgcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MRGCN_REQUIRE(h > 0 && n >= 0 && N < (1ll << 31) && NR < (1ll << 31) && n < (1ll << 29), MRGCN_E_BADARG,
+                "distmult_bwd: bad sizes");
+  if (gE) MRGCN_CUDA(cudaMemsetAsync(gE, 0, sizeof(float) * (size_t)N * h, st));
+  if (gRel) MRGCN_CUDA(cudaMemsetAsync(gRel, 0, sizeof(float) * (size_t)NR * h, st));
+  if (n == 0) return 0;
+  int32_t *nk = ws, *nko = ws + 2 * n, *nv = ws + 4 * n, *nvo = ws + 6 * n;
+  int32_t *pk = ws + 8 * n, *pko = ws + 9 * n, *pv = ws + 10 * n, *pvo = ws + 11 * n;
+  k_incidence<<<(unsigned)cdiv(n, kThreads), kThreads, 0, st>>>(s, p, o, n, nk, nv, pk, pv);
+  MRGCN_LAUNCH_CHECK();
+  if (gE) {
+    if (int rc = sort_i32(nk, nko, nv, nvo, 2 * n, st)) return rc;
+    MRGCN_PROF("distmult_bwd_nodes");
+  k_distmult_bwd_nodes<<<(unsigned)cdiv(2 * n * 32, kThreads), kThreads, 0, st>>>(nko, nvo, 2 * n, n, s, p, o, gscore, E,
+                                                                                    Rel, h, gE);
+    MRGCN_LAUNCH_CHECK();
+  }
+  if (gRel) {
+    if (int rc = sort_i32(pk, pko, pv, pvo, n, st)) return rc;
+    MRGCN_PROF("distmult_bwd_rels");
+  k_distmult_bwd_rels<<<(unsigned)cdiv(n * 32, kThreads), kThreads, 0, st>>>(pko, pvo, n, s, o, gscore, E, h, gRel);
+    MRGCN_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int mrgcn_distmult_rank(const int64_t *facts, int64_t F, int32_t head, const float *E, const float *Rel,
+                                   int64_t N, int32_t h, const int32_t *filt_ptr, const int32_t *filt_idx,
+                                   float *scores_ws, int64_t *rank, mrgcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MRGCN_REQUIRE(F >= 0 && N > 0 && h > 0 && scores_ws && rank, MRGCN_E_BADARG, "distmult_rank: bad arguments");
+  MRGCN_REQUIRE(F < 65536, MRGCN_E_BADARG, "distmult_rank: at most 65535 facts per call");
+  if (F == 0) return 0;
+  dim3 grid((unsigned)cdiv(N, 64), (unsigned)F);
+  MRGCN_PROF("rank_scores");
+  k_rank_scores<<<grid, kThreads, 2 * h * sizeof(float), st>>>(facts, head, E, Rel, N, h, scores_ws);
+  MRGCN_LAUNCH_CHECK();
+  if (filt_ptr && filt_idx) {
+    k_rank_filter<<<(unsigned)F, 128, 0, st>>>(facts, head, filt_ptr, filt_idx, N, scores_ws);
+    MRGCN_LAUNCH_CHECK();
+  }
+  MRGCN_PROF("rank_count");
+  k_rank_count<<<(unsigned)F, kThreads, 0, st>>>(facts, head, N, scores_ws, rank);
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}

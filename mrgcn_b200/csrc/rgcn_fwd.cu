@@ -1,0 +1,411 @@
+// R-GCN layer forward (replaces GraphConvolution.forward, /root/reference/mrgcn/layers/graph.py:62-102,
+// and the mask/ReLU lines of RGCN._forward_full_batch, mrgcn/models/rgcn.py:78-87).
+//
+// The reference materialises one dense operand row per (relation, node) -- R*N*out floats -- and
+// calls torch.mm(sparse COO, dense).  Here nothing of size R*N*out exists:
+//   identity term, B>0 : source-major pass (E2).  A CTA stages the basis rows V_I[:, j0:j0+TJ, :] of TJ
+//                        consecutive sources ONCE in shared memory (coalesced runs per basis), mixes them
+//                        with comp_I[r,:] per edge and writes one `out`-wide message per edge.
+//   feature term       : relation-major pass (E3).  A CTA stages W_F(r) once per chunk of edges of one
+//                        relation and computes val * X[j,:] . W_F(r) per edge (rows of X staged through
+//                        shared memory with coalesced loads).
+//   aggregation        : destination-major pass (E1).  Deterministic segmented sum of the messages of a
+//                        row (+ the direct weight_I row gather when B == 0) fused with bias, row mask, ReLU.
+// All passes are HBM/L2-bound gathers; there is no float atomic anywhere.
+#include "common.cuh"
+
+namespace mrgcn {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// W[r, x] = sum_b comp[r,b] * V[b, x]   (graph.py:83-85; x over in*out).  Tiny.
+__global__ void k_basis_mix_fwd(const float *__restrict__ comp, const float *__restrict__ V, float *__restrict__ W,
+                                int B, int IO) {
+  int r = blockIdx.y;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= IO) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc = fmaf(__ldg(comp + (size_t)r * B + b), __ldg(V + (size_t)b * IO + x), acc);
+  W[(size_t)r * IO + x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Identity term with basis decomposition (graph.py:69-75), source-major.
+//   msg[e2, :] = val_e * sum_b comp[r_e, b] * V[b, j_e, :]
+// smem: comp_s[R][CS] (CS odd -> lanes with different relations hit different banks) then
+//       Vs[B][TJ][OP] (OP = out rounded up to a multiple of OC; rows 16B aligned for LDS.128).
+template <int OC>
+__global__ void __launch_bounds__(kThreads)
+k_ident_msg_fwd(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
+                const int32_t *__restrict__ e2_src, const int32_t *__restrict__ e2_rel,
+                const float *__restrict__ e2_val, float *__restrict__ msg, int NS, int R, int B, int out, int OP,
+                int TJ, int CS, int comp_smem) {
+  extern __shared__ __align__(16) float smem[];
+  float *comp_s = smem;
+  float *Vs = smem + (comp_smem ? ((R * CS + 3) & ~3) : 0);
+  const int tid = threadIdx.x;
+  if (comp_smem) {
+    for (int r = tid / 32; r < R; r += kThreads / 32)
+      for (int b = tid & 31; b < B; b += 32) comp_s[r * CS + b] = __ldg(comp + (size_t)r * B + b);
+  }
+  // persistent: a CTA walks tiles of TJ consecutive sources (comp stays resident)
+  for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
+    const int tjw = min(TJ, NS - j0);
+    const int e_lo = colptr[j0], e_hi = colptr[j0 + tjw];
+    if (e_lo == e_hi) continue;
+    __syncthreads();  // previous tile fully consumed (and comp_s visible)
+    // stage the tile: for every basis one contiguous run of tjw*out floats
+    const int run = tjw * out;
+    for (int x = tid; x < run; x += kThreads) {
+      int jl = x / out, o = x - jl * out;
+      const float *src = V + (size_t)j0 * out + x;
+      float *dst = Vs + jl * OP + o;
+#pragma unroll 8
+      for (int b = 0; b < B; ++b) dst[(size_t)b * TJ * OP] = ldg_stream(src + (size_t)b * NS * out);
+    }
+    __syncthreads();
+    for (int e = e_lo + tid; e < e_hi; e += kThreads) {
+      const int jl = e2_src[e] - j0, r = e2_rel[e];
+      const float v = e2_val[e];
+      const float *cr = comp_smem ? comp_s + r * CS : comp + (size_t)r * B;
+      for (int c0 = 0; c0 < OP; c0 += OC) {
+        float acc[OC];
+#pragma unroll
+        for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+        const float *vp = Vs + jl * OP + c0;
+        for (int b = 0; b < B; ++b) {
+          const float c = cr[b];
+          const float4 *v4 = reinterpret_cast<const float4 *>(vp + (size_t)b * TJ * OP);
+#pragma unroll
+          for (int q = 0; q < OC / 4; ++q) {
+            float4 t = v4[q];
+            acc[4 * q + 0] = fmaf(c, t.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(c, t.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(c, t.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(c, t.w, acc[4 * q + 3]);
+          }
+        }
+        float *mp = msg + (size_t)e * out + c0;
+#pragma unroll
+        for (int o = 0; o < OC; ++o)
+          if (c0 + o < out) mp[o] = v * acc[o];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Feature term (graph.py:93-95 re-associated: no (R,N,out) projection), relation-major.
+//   msg[e3, :] = val_e * X[j_e, :] . W[r, :, :]          one CTA = one chunk of edges of ONE relation
+// smem: Ws[INP][OC] for the current output chunk (INP = in rounded up to KC, pad rows zero),
+//       Xs[warp][32][KC+1] staging of X rows (coalesced loads, conflict-free column reads).
+constexpr int KC = 32;
+template <int OC>
+__global__ void __launch_bounds__(kThreads)
+k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const int32_t *__restrict__ chunk_rel,
+               const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ e3_src,
+               const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {
+  extern __shared__ __align__(16) float smem[];
+  float *Ws = smem;                         // [INP][OC]
+  float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][32][KC+1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = kThreads / 32;
+  float *Xs = Xs_all + (size_t)warp * 32 * (KC + 1);
+  const int c = blockIdx.x;
+  const int r = chunk_rel[c];
+  const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
+  const float *Wr = W + (size_t)r * in * out;
+  for (int c0 = 0; c0 < out; c0 += OC) {
+    __syncthreads();
+    for (int x = tid; x < INP * OC; x += kThreads) {
+      int k = x / OC, o = x - k * OC;
+      Ws[x] = (k < in && c0 + o < out) ? __ldg(Wr + (size_t)k * out + c0 + o) : 0.f;
+    }
+    __syncthreads();
+    for (int eb = e_lo + warp * 32; eb < e_hi; eb += nwarps * 32) {
+      const int e = eb + lane;
+      const bool live = e < e_hi;
+      const int j = live ? e3_src[e] : -1;
+      float acc[OC];
+#pragma unroll
+      for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+      for (int k0 = 0; k0 < in; k0 += KC) {
+        __syncwarp();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          int ji = __shfl_sync(0xffffffffu, j, i);
+          float x = 0.f;
+          if (ji >= 0 && k0 + lane < in) x = X[(size_t)ji * in + k0 + lane];
+          Xs[i * (KC + 1) + lane] = x;
+        }
+        __syncwarp();
+        const float *xrow = Xs + lane * (KC + 1);
+        const float *wk = Ws + (size_t)k0 * OC;
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+          const float x = xrow[kk];
+          const float4 *w4 = reinterpret_cast<const float4 *>(wk + kk * OC);
+#pragma unroll
+          for (int q = 0; q < OC / 4; ++q) {
+            float4 t = w4[q];
+            acc[4 * q + 0] = fmaf(x, t.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x, t.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x, t.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x, t.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      if (live) {
+        const float v = e3_val[e];
+        float *mp = msg + (size_t)e * out + c0;
+#pragma unroll
+        for (int o = 0; o < OC; ++o)
+          if (c0 + o < out) mp[o] = v * acc[o];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Aggregation over destination rows (E1), fused with bias, row mask and ReLU.
+struct AggArgs {
+  const int32_t *rowptr;
+  const int32_t *pI;   // e1_to_e2 of gI (messages of the identity term) or NULL
+  const float *msgI;
+  const int32_t *pF;   // e1_to_e3 of gF or NULL
+  const float *msgF;
+  const int32_t *rowptrF;  // rowptr of gF (== rowptr when gI == gF)
+  const float *Wd;     // weight_I for the direct gather (B == 0) or NULL
+  const int32_t *d_src, *d_rel;
+  const float *d_val;
+  int64_t NSd;
+  const float *bias, *mask;
+  float *out;
+  int ND, odim, relu, thresh;
+};
+
+__device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int beg, int end, int step) {
+  float acc = 0.f;
+  const int od = a.odim;
+  int lo = a.rowptr ? a.rowptr[i] : 0, hi = a.rowptr ? a.rowptr[i + 1] : 0;
+  if (a.msgI) {
+    for (int e = lo + beg; e < hi; e += step) acc += a.msgI[(size_t)a.pI[e] * od + o];
+  }
+  if (a.Wd) {
+    for (int e = lo + beg; e < hi; e += step)
+      acc = fmaf(a.d_val[e], a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o], acc);
+  }
+  if (a.msgF) {
+    int lf = a.rowptrF[i], hf = a.rowptrF[i + 1];
+    for (int e = lf + beg; e < hf; e += step) acc += a.msgF[(size_t)a.pF[e] * od + o];
+  }
+  (void)end;
+  return acc;
+}
+
+__device__ __forceinline__ int row_degree(const AggArgs &a, int i) {
+  int d = 0;
+  if (a.rowptr) d = a.rowptr[i + 1] - a.rowptr[i];
+  if (a.msgF) d = max(d, a.rowptrF[i + 1] - a.rowptrF[i]);
+  return d;
+}
+
+__device__ __forceinline__ void agg_store(const AggArgs &a, int i, int o, float acc) {
+  if (a.bias) acc += a.bias[o];
+  if (a.mask) acc *= a.mask[i];
+  if (a.relu) acc = fmaxf(acc, 0.f);
+  a.out[(size_t)i * a.odim + o] = acc;
+}
+
+// short rows: one sub-warp group of `odim` lanes per row (32/odim rows per warp), or a whole warp per row
+__global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
+  const int od = a.odim;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  if (od >= 32) {
+    int i = gw;
+    if (i >= a.ND) return;
+    if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
+    for (int o = lane; o < od; o += 32) agg_store(a, i, o, agg_edges(a, i, o, 0, 0, 1));
+  } else {
+    const int rpw = 32 / od;
+    const int slot = lane / od, o = lane - slot * od;
+    int i = gw * rpw + slot;
+    if (slot >= rpw || i >= a.ND) return;
+    if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
+    agg_store(a, i, o, agg_edges(a, i, o, 0, 0, 1));
+  }
+}
+
+// long rows (hubs): one CTA per row, edge slots strided over the row, fixed-order tree over slots
+__global__ void __launch_bounds__(kThreads) k_agg_fwd_long(AggArgs a, const int32_t *__restrict__ long_rows) {
+  extern __shared__ float red[];  // [nslots][oc]
+  const int od = a.odim;
+  const int i = long_rows[blockIdx.x];
+  const int oc = min(od, kThreads);
+  const int nslots = kThreads / oc;
+  const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
+  for (int o0 = 0; o0 < od; o0 += oc) {
+    const int o = o0 + ol;
+    float acc = 0.f;
+    if (slot < nslots && o < od) acc = agg_edges(a, i, o, slot, 0, nslots);
+    if (slot < nslots) red[slot * oc + ol] = acc;
+    __syncthreads();
+    for (int s = 1; s < nslots; s <<= 1) {
+      if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
+      __syncthreads();
+    }
+    if (slot == 0 && o < od) agg_store(a, i, o, red[ol]);
+    __syncthreads();
+  }
+}
+
+template <class K>
+static unsigned persistent_grid(K kernel, int threads, size_t smem, int64_t max_ctas) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)kNumSMs * per_sm;
+  return (unsigned)(g < max_ctas ? g : (max_ctas > 0 ? max_ctas : 1));
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) MRGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+}  // namespace
+
+// ---- launchers (also used by rgcn_bwd.cu) ------------------------------------------------------
+int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(IO, 128), (unsigned)R);
+  MRGCN_PROF("basis_mix_fwd");
+  k_basis_mix_fwd<<<grid, 128, 0, st>>>(comp, V, W, B, IO);
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+int pick_oc(int out) { return out <= 4 ? 4 : out <= 8 ? 8 : out <= 12 ? 12 : 16; }
+
+// tile of sources for the identity-term kernels: tjw*out <= 256 (one coalesced run per basis), smem bounded
+int ident_tile(int B, int out, int OP) {
+  int tj = 256 / out;
+  if (tj < 1) tj = 1;
+  while (tj > 1 && (size_t)B * tj * OP * 4 > 56 * 1024) --tj;
+  return tj;
+}
+
+static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const float *comp, float *msg, int B, int out,
+                                cudaStream_t st) {
+  const int OC = pick_oc(out);
+  const int OP = (int)cdiv(out, OC) * OC;
+  const int TJ = ident_tile(B, out, OP);
+  const int CS = B | 1;
+  const int comp_smem = ((size_t)g->R * CS * 4 <= 64 * 1024) ? 1 : 0;
+  size_t smem = (comp_smem ? (((size_t)g->R * CS + 3) & ~(size_t)3) : 0) * 4 + (size_t)B * TJ * OP * 4;
+  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "ident_msg_fwd: B*out too large for shared memory (%zu B)", smem);
+  unsigned grid = 0;
+#define LAUNCH(OCV)                                                                                               \
+  do {                                                                                                            \
+    if (int rc = set_smem(k_ident_msg_fwd<OCV>, smem)) return rc;                                                 \
+    grid = persistent_grid(k_ident_msg_fwd<OCV>, kThreads, smem, cdiv(g->NS, TJ));                                \
+    k_ident_msg_fwd<OCV><<<grid, kThreads, smem, st>>>(V, comp, g->colptr, g->e2_src, g->e2_rel, g->e2_val, msg, \
+                                                       g->NS, g->R, B, out, OP, TJ, CS, comp_smem);              \
+  } while (0)
+  MRGCN_PROF("ident_msg_fwd");
+  switch (OC) {
+    case 4: LAUNCH(4); break;
+    case 8: LAUNCH(8); break;
+    case 12: LAUNCH(12); break;
+    default: LAUNCH(16); break;
+  }
+#undef LAUNCH
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_feat_msg_fwd(const mrgcn_graph *g, const float *X, const float *W, float *msg, int in, int out,
+                               cudaStream_t st) {
+  if (g->n_chunks == 0) return 0;
+  const int OC = pick_oc(out);
+  const int INP = (int)cdiv(in, KC) * KC;
+  size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 32 * (KC + 1)) * 4;
+  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "feat_msg_fwd: in too large for shared memory (%zu B)", smem);
+#define LAUNCH(OCV)                                                                                            \
+  do {                                                                                                         \
+    if (int rc = set_smem(k_feat_msg_fwd<OCV>, smem)) return rc;                                               \
+    k_feat_msg_fwd<OCV><<<(unsigned)g->n_chunks, kThreads, smem, st>>>(X, W, g->chunk_rel, g->chunk_ptr,      \
+                                                                      g->e3_src, g->e3_val, msg, in, out, INP); \
+  } while (0)
+  MRGCN_PROF("feat_msg_fwd");
+  switch (OC) {
+    case 4: LAUNCH(4); break;
+    case 8: LAUNCH(8); break;
+    case 12: LAUNCH(12); break;
+    default: LAUNCH(16); break;
+  }
+#undef LAUNCH
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mrgcn
+
+using namespace mrgcn;
+
+extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  MRGCN_REQUIRE(a && a->out && a->out_dim > 0, MRGCN_E_BADARG, "layer_fwd: null/empty output");
+  const bool hasI = a->weight_I != nullptr, hasF = a->X != nullptr;
+  MRGCN_REQUIRE(hasI || hasF, MRGCN_E_BADARG, "layer_fwd: neither identity nor feature term");
+  MRGCN_REQUIRE(!hasI || a->gI, MRGCN_E_BADARG, "layer_fwd: identity term without graph");
+  MRGCN_REQUIRE(!hasF || (a->gF && a->weight_F && a->in_dim > 0), MRGCN_E_BADARG, "layer_fwd: feature term incomplete");
+  const int B = a->B > 0 ? a->B : 0, out = a->out_dim, in = a->in_dim;
+  const mrgcn_graph *gI = a->gI, *gF = a->gF;
+  const int ND = hasI ? gI->ND : gF->ND;
+  MRGCN_REQUIRE(!(hasI && hasF) || gI->ND == gF->ND, MRGCN_E_BADARG, "layer_fwd: graphs disagree on rows");
+
+  AggArgs g{};
+  g.ND = ND; g.odim = out; g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.out = a->out;
+  const mrgcn_graph *gl = hasI ? gI : gF;  // long-row list owner
+  if (hasI) {
+    g.rowptr = gI->rowptr;
+    if (B > 0) {
+      MRGCN_REQUIRE(a->comp_I && a->msg_I, MRGCN_E_BADARG, "layer_fwd: comp_I/msg_I missing");
+      if (gI->E > 0)
+        if (int rc = launch_ident_msg_fwd(gI, a->weight_I, a->comp_I, a->msg_I, B, out, st)) return rc;
+      g.pI = gI->e1_to_e2; g.msgI = a->msg_I;
+    } else {
+      g.Wd = a->weight_I; g.d_src = gI->e1_src; g.d_rel = gI->e1_rel; g.d_val = gI->e1_val; g.NSd = gI->NS;
+    }
+  }
+  if (hasF) {
+    const float *W = a->weight_F;
+    if (B > 0) {
+      MRGCN_REQUIRE(a->comp_F && a->wmix, MRGCN_E_BADARG, "layer_fwd: comp_F/wmix missing");
+      if (int rc = launch_basis_mix_fwd(a->comp_F, a->weight_F, a->wmix, gF->R, B, in * out, st)) return rc;
+      W = a->wmix;
+    }
+    MRGCN_REQUIRE(a->msg_F, MRGCN_E_BADARG, "layer_fwd: msg_F missing");
+    if (gF->E > 0)
+      if (int rc = launch_feat_msg_fwd(gF, a->X, W, a->msg_F, in, out, st)) return rc;
+    g.pF = gF->e1_to_e3; g.msgF = a->msg_F; g.rowptrF = gF->rowptr;
+  }
+  // long rows are those of either graph; the host side builds the union list on the owner graph
+  g.thresh = gl->n_long_rows > 0 ? gl->long_row_thresh : 0;
+  const int rows_per_warp = out >= 32 ? 1 : 32 / out;
+  unsigned grid = (unsigned)cdiv(cdiv(ND, rows_per_warp) * 32, kThreads);
+  if (ND > 0) {
+    MRGCN_PROF("agg_fwd");
+  k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
+    MRGCN_LAUNCH_CHECK();
+    if (gl->n_long_rows > 0) {
+      MRGCN_PROF("agg_fwd_long");
+  k_agg_fwd_long<<<(unsigned)gl->n_long_rows, kThreads, kThreads * sizeof(float), st>>>(g, gl->long_rows);
+      MRGCN_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}

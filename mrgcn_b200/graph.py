@@ -1,0 +1,166 @@
+"""Device-resident relational graph: the reference's stacked adjacency re-emitted as three sorted
+edge orders (include/mrgcn_b200.h).
+
+The reference hands its layer a torch sparse COO tensor `A` of shape (rows, R*N) built by
+`scipy_sparse_to_pytorch_sparse` (/root/reference/mrgcn/data/utils.py:165-170, called with int8 from
+mrgcn/data/batch.py:144-149) and lets `torch.mm` re-sort it on every call.  `RelGraph.from_coo`
+consumes exactly that tensor once (values are taken from the tensor as handed over, so the int8
+truncation of the reference is reproduced bit for bit) and `graph_of(A, R)` caches the result on the
+tensor object, whose lifetime is that of the batch (batches are built once and reused every epoch,
+mrgcn/tasks/node_classification.py:128-134).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nv
+
+LONG_THRESH = 512      # rows / sources with more edges than this get a CTA of their own
+_I32 = torch.int32
+
+
+def _chunk_size(E):
+    # E3 chunks: enough of them to fill 148 SMs several times over, large enough to amortise staging
+    ch = E // (148 * 24)
+    return int(min(1024, max(128, (ch // 32) * 32)))
+
+
+class RelGraph:
+    """E1/E2/E3 edge orders of one adjacency on one CUDA device."""
+
+    def __init__(self, E, ND, NS, R, device):
+        self.E, self.ND, self.NS, self.R, self.device = int(E), int(ND), int(NS), int(R), device
+        e = max(self.E, 1)
+        mk_i = lambda n: torch.empty(n, dtype=_I32, device=device)
+        mk_f = lambda n: torch.empty(n, dtype=torch.float32, device=device)
+        self.rowptr, self.colptr, self.relptr = mk_i(ND + 1), mk_i(NS + 1), mk_i(R + 1)
+        self.e1_src, self.e1_rel, self.e1_val = mk_i(e), mk_i(e), mk_f(e)
+        self.e1_to_e2, self.e1_to_e3 = mk_i(e), mk_i(e)
+        self.e2_src, self.e2_dst, self.e2_rel, self.e2_val = mk_i(e), mk_i(e), mk_i(e), mk_f(e)
+        self.e3_src, self.e3_dst, self.e3_val, self.e3_to_e2 = mk_i(e), mk_i(e), mk_f(e), mk_i(e)
+        self.long_rows = self.long_cols = None
+        self.chunk_rel = self.chunk_ptr = self.rel_chunk_ptr = None
+        self.n_chunks = 0
+        self.c = nv.Graph()
+
+    # ------------------------------------------------------------------------------------------
+    def _fill_struct(self):
+        c = self.c
+        c.E, c.ND, c.NS, c.R = self.E, self.ND, self.NS, self.R
+        for name in ("rowptr", "e1_src", "e1_rel", "e1_val", "e1_to_e2", "e1_to_e3", "colptr", "e2_src", "e2_dst",
+                     "e2_rel", "e2_val", "relptr", "e3_src", "e3_dst", "e3_val", "e3_to_e2"):
+            setattr(c, name, getattr(self, name).data_ptr())
+
+    def _build_worklists(self, chunk=None):
+        """Hub lists and the relation-chunk work list (host side; one sync, at build time only)."""
+        dev = self.device
+        deg_r = self.rowptr[1:] - self.rowptr[:-1]
+        deg_c = self.colptr[1:] - self.colptr[:-1]
+        self.long_rows = torch.nonzero(deg_r > LONG_THRESH).flatten().to(_I32)
+        self.long_cols = torch.nonzero(deg_c > LONG_THRESH).flatten().to(_I32)
+        relptr = self.relptr.cpu().numpy().astype(np.int64)
+        ch = chunk or _chunk_size(self.E)
+        cnt = np.diff(relptr)
+        nch = (cnt + ch - 1) // ch
+        rel_chunk_ptr = np.zeros(self.R + 1, dtype=np.int64)
+        np.cumsum(nch, out=rel_chunk_ptr[1:])
+        n_chunks = int(rel_chunk_ptr[-1])
+        chunk_rel = np.repeat(np.arange(self.R), nch)
+        within = np.arange(n_chunks) - rel_chunk_ptr[chunk_rel]
+        lo = relptr[chunk_rel] + within * ch
+        chunk_ptr = np.empty(n_chunks + 1, dtype=np.int64)
+        chunk_ptr[:-1] = lo
+        chunk_ptr[-1] = relptr[-1]
+        # a chunk ends where the next begins or where its relation ends
+        if n_chunks:
+            hi = np.minimum(lo + ch, relptr[chunk_rel + 1])
+            assert np.array_equal(hi[:-1], chunk_ptr[1:-1]) and hi[-1] == chunk_ptr[-1]
+        self.chunk_size = ch
+        self.n_chunks = n_chunks
+        self.chunk_rel = torch.from_numpy(chunk_rel.astype(np.int32)).to(dev) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
+        self.chunk_ptr = torch.from_numpy(chunk_ptr.astype(np.int32)).to(dev)
+        self.rel_chunk_ptr = torch.from_numpy(rel_chunk_ptr.astype(np.int32)).to(dev)
+        c = self.c
+        c.long_rows = self.long_rows.data_ptr() if len(self.long_rows) else None
+        c.n_long_rows, c.long_row_thresh = len(self.long_rows), LONG_THRESH
+        c.long_cols = self.long_cols.data_ptr() if len(self.long_cols) else None
+        c.n_long_cols, c.long_col_thresh = len(self.long_cols), LONG_THRESH
+        c.chunk_rel, c.chunk_ptr = self.chunk_rel.data_ptr(), self.chunk_ptr.data_ptr()
+        c.rel_chunk_ptr, c.n_chunks = self.rel_chunk_ptr.data_ptr(), n_chunks
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def from_coo_arrays(cls, row, col, val, nrows, ncols, R, chunk=None):
+        """row, col: int64 CUDA tensors; val: float32 CUDA tensor (already the values `A.float()` would give)."""
+        for t, n in ((row, "row"), (col, "col"), (val, "val")):
+            nv.require_cuda(t, n)
+        if ncols % R:
+            raise ValueError("adjacency has %d columns, not a multiple of num_relations=%d" % (ncols, R))
+        row, col, val = row.contiguous(), col.contiguous(), val.contiguous().float()
+        g = cls(row.numel(), nrows, ncols // R, R, row.device)
+        g._fill_struct()
+        with torch.cuda.device(row.device):
+            nv.check(nv.lib().mrgcn_graph_build(nv.ptr(row), nv.ptr(col), nv.ptr(val), g.E, nrows, ncols, R,
+                                                C.byref(g.c), nv.stream_ptr()), "graph_build")
+            g._build_worklists(chunk)
+        return g
+
+    @classmethod
+    def from_coo(cls, A, R, device=None, chunk=None):
+        """A: torch sparse COO (int8 as the reference makes it, or float), CPU or CUDA; shape (rows, R*NS)."""
+        if A.layout != torch.sparse_coo:
+            raise TypeError("expected a torch sparse COO tensor (mrgcn/data/utils.py:165-170)")
+        device = torch.device(device) if device is not None else (A.device if A.is_cuda else torch.device("cuda"))
+        idx = A._indices().to(device, non_blocking=True)
+        val = A._values().to(device, non_blocking=True).float()     # graph.py:75 `A.float()`: exact for int8
+        return cls.from_coo_arrays(idx[0], idx[1], val, A.shape[0], A.shape[1], R, chunk)
+
+    @classmethod
+    def from_triples(cls, triples, num_nodes, num_props, include_inverse=True, device="cuda", chunk=None):
+        """Integer triples (s,p,o) -> normalised stacked adjacency built on the GPU, bit-exact with
+        mrgcn/encodings/graph_structure.py:70-108,162-169 + the float32 cast of tarball.py:151-157."""
+        device = torch.device(device)
+        tr = torch.as_tensor(np.ascontiguousarray(triples, dtype=np.int32)).to(device)
+        T = tr.shape[0]
+        R = (2 * num_props if include_inverse else num_props) + 1
+        n = (2 * T if include_inverse else T) + num_nodes
+        row = torch.empty(n, dtype=torch.int64, device=device)
+        col = torch.empty(n, dtype=torch.int64, device=device)
+        val = torch.empty(n, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            nv.check(nv.lib().mrgcn_adjacency_from_triples(nv.ptr(tr), T, num_nodes, num_props, int(include_inverse),
+                                                           nv.ptr(row), nv.ptr(col), nv.ptr(val), nv.stream_ptr()),
+                     "adjacency_from_triples")
+        g = cls.from_coo_arrays(row, col, val, num_nodes, R * num_nodes, R, chunk)
+        g.coo = (row, col, val)
+        return g
+
+    def to_coo(self, dtype=torch.float32):
+        """Back to a (coalesced-order) torch sparse COO on the device: E1 order, column = rel*NS + src."""
+        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
+        row = torch.repeat_interleave(torch.arange(self.ND, device=self.device), deg)
+        col = self.e1_rel[:self.E].long() * self.NS + self.e1_src[:self.E].long()
+        return torch.sparse_coo_tensor(torch.stack([row, col]), self.e1_val[:self.E].to(dtype), (self.ND, self.R * self.NS))
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if isinstance(t, torch.Tensor))
+
+
+def graph_of(A, R, device=None):
+    """RelGraph of a reference-style sparse COO tensor, cached on the tensor object itself."""
+    if isinstance(A, RelGraph):
+        return A
+    cache = getattr(A, "_mrgcn_b200_graph", None)
+    dev = torch.device(device) if device is not None else None
+    if cache is not None and cache[0] == (R, A._version, A._nnz()) and (dev is None or cache[1].device == dev or
+                                                                         (dev.index is None and cache[1].device.type == dev.type)):
+        return cache[1]
+    g = RelGraph.from_coo(A, R, device)
+    try:
+        A._mrgcn_b200_graph = ((R, A._version, A._nnz()), g)
+    except Exception:   # tensors that refuse attributes: rebuild per call
+        pass
+    return g

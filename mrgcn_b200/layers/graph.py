@@ -1,0 +1,197 @@
+"""R-GCN layer: same constructor, parameters, state_dict and forward signature as the reference's
+`mrgcn.layers.graph.GraphConvolution` (/root/reference/mrgcn/layers/graph.py:8-116); the arithmetic
+runs in hand-written sm_100a kernels behind the C ABI (include/mrgcn_b200.h).  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _native as nv
+from ..graph import RelGraph, graph_of
+
+
+def _empty(n, like_dev):
+    return torch.empty(max(int(n), 1), dtype=torch.float32, device=like_dev)
+
+
+class _LayerFn(torch.autograd.Function):
+    """out = act(mask * (b + A.W_I(mixed) + A.(X W_F(mixed))))  — graph.py:62-102 + rgcn.py:78-87."""
+
+    @staticmethod
+    def forward(ctx, X, weight_I, comp_I, weight_F, comp_F, bias, row_mask, gI, gF, B, relu):
+        hasI, hasF = weight_I is not None, X is not None
+        ref = weight_I if hasI else weight_F
+        dev = ref.device
+        out_dim = ref.shape[-1]
+        in_dim = weight_F.shape[1] if hasF else 0
+        B = int(B) if B and B > 0 else 0
+        g0 = gI if hasI else gF
+        tens = dict(X=X, weight_I=weight_I, comp_I=comp_I if (hasI and B) else None,
+                    weight_F=weight_F if hasF else None, comp_F=comp_F if (hasF and B) else None,
+                    bias=bias, row_mask=row_mask)
+        for k, t in tens.items():
+            if t is not None:
+                nv.require_cuda(t, k)
+                if t.dtype != torch.float32:
+                    raise TypeError("mrgcn_b200: %s must be float32" % k)
+                tens[k] = t.contiguous()
+        if hasF and tens["X"].shape != (gF.NS, in_dim):
+            raise ValueError("X has shape %s, expected (%d, %d)" % (tuple(X.shape), gF.NS, in_dim))
+        if hasI and weight_I.shape[0] != (B if B else gI.R) * gI.NS:
+            raise ValueError("weight_I has %d rows, expected %d" % (weight_I.shape[0], (B if B else gI.R) * gI.NS))
+        out = torch.empty((g0.ND, out_dim), dtype=torch.float32, device=dev)
+        wmix = _empty(gF.R * in_dim * out_dim, dev) if (hasF and B) else None
+        msg_I = _empty(gI.E * out_dim, dev) if (hasI and B) else None
+        msg_F = _empty(gF.E * out_dim, dev) if hasF else None
+        a = nv.LayerArgs()
+        a.gI = C.pointer(gI.c) if hasI else None
+        a.gF = C.pointer(gF.c) if hasF else None
+        a.in_dim, a.out_dim, a.B, a.relu = in_dim, out_dim, B, int(bool(relu))
+        for k, t in tens.items():
+            setattr(a, k, nv.ptr(t))
+        a.wmix, a.msg_I, a.msg_F, a.out = nv.ptr(wmix), nv.ptr(msg_I), nv.ptr(msg_F), nv.ptr(out)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().mrgcn_rgcn_layer_fwd(C.byref(a), nv.stream_ptr()), "rgcn_layer_fwd")
+        ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims = gI, gF, B, bool(relu), (in_dim, out_dim)
+        ctx.save_for_backward(tens["X"], tens["weight_I"], tens["comp_I"], tens["weight_F"], tens["comp_F"],
+                              tens["bias"], tens["row_mask"], wmix, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, weight_I, comp_I, weight_F, comp_F, bias, row_mask, wmix, out = ctx.saved_tensors
+        gI, gF, B = ctx.gI, ctx.gF, ctx.B
+        in_dim, out_dim = ctx.dims
+        hasI, hasF = weight_I is not None, X is not None
+        dev = out.device
+        gout = gout.contiguous().float()
+        need = ctx.needs_input_grad
+        b = nv.LayerBwdArgs()
+        f = b.f
+        f.gI = C.pointer(gI.c) if hasI else None
+        f.gF = C.pointer(gF.c) if hasF else None
+        f.in_dim, f.out_dim, f.B, f.relu = in_dim, out_dim, B, int(ctx.relu)
+        f.weight_I, f.comp_I, f.X, f.weight_F, f.comp_F = (nv.ptr(weight_I), nv.ptr(comp_I), nv.ptr(X),
+                                                           nv.ptr(weight_F), nv.ptr(comp_F))
+        f.bias, f.row_mask, f.wmix, f.out = nv.ptr(bias), nv.ptr(row_mask), nv.ptr(wmix), nv.ptr(out)
+        g0 = gI if hasI else gF
+        gact = _empty(g0.ND * out_dim, dev)
+        g_wI = g_cI = g_wF = g_cF = g_b = g_X = None
+        cbuf = g_wmix = None
+        part_elems = 1
+        if hasI and (need[1] or need[2]):
+            g_wI = torch.empty_like(weight_I)
+            if B:
+                g_cI = torch.empty_like(comp_I)
+                cbuf = _empty(gI.E * B, dev)
+                part_elems = max(part_elems, gI.n_chunks * B)
+        if hasF and (need[3] or need[4]):
+            g_wF = torch.empty_like(weight_F)
+            part_elems = max(part_elems, gF.n_chunks * in_dim * out_dim)
+            if B:
+                g_cF = torch.empty_like(comp_F)
+                g_wmix = _empty(gF.R * in_dim * out_dim, dev)
+        if hasF and need[0]:
+            g_X = torch.empty_like(X)
+        colsum = None
+        if bias is not None and need[5]:
+            g_b = torch.empty_like(bias)
+            colsum = _empty(((g0.ND + 1023) // 1024) * out_dim, dev)
+        part = _empty(part_elems, dev)
+        b.gout = nv.ptr(gout)
+        b.g_weight_I, b.g_comp_I, b.g_weight_F, b.g_comp_F = nv.ptr(g_wI), nv.ptr(g_cI), nv.ptr(g_wF), nv.ptr(g_cF)
+        b.g_bias, b.g_X = nv.ptr(g_b), nv.ptr(g_X)
+        b.gact, b.cbuf, b.part, b.g_wmix, b.colsum_ws = nv.ptr(gact), nv.ptr(cbuf), nv.ptr(part), nv.ptr(g_wmix), nv.ptr(colsum)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
+        return (g_X, g_wI, g_cI, g_wF, g_cF, g_b, None, None, None, None, None)
+
+
+def slice_columns_device(A, A_idx, device):
+    """`sliceSparseCOO` (/root/reference/mrgcn/data/batch.py:252-263) on the device: keep the entries whose
+    column is in A_idx, renumber columns by position in A_idx, reset every kept value to 1.0 (float32)."""
+    ind = A._indices().to(device)
+    col_idx = torch.as_tensor(A_idx, dtype=torch.int64, device=device)
+    order = torch.argsort(col_idx, stable=True)
+    sorted_cols = col_idx[order]
+    pos = torch.searchsorted(sorted_cols, ind[1]).clamp_(max=max(len(col_idx) - 1, 0))
+    keep = sorted_cols[pos] == ind[1] if len(col_idx) else torch.zeros_like(ind[1], dtype=torch.bool)
+    row, col = ind[0][keep], order[pos[keep]]
+    return row, col, torch.ones(len(row), dtype=torch.float32, device=device)
+
+
+class GraphConvolution(nn.Module):
+    """Relational graph convolution layer (drop-in for mrgcn.layers.graph.GraphConvolution).
+
+    Parameters, their shapes, registration order (weight_I_comp, weight_F_comp, weight_I, weight_F, b) and
+    initialisation follow graph.py:9-60,104-116, so the same seed gives the same initial state_dict.
+    """
+
+    def __init__(self, indim, outdim, num_relations, num_nodes, num_bases=-1, bias=False, input_layer=False,
+                 featureless=False, shared_bases_weights=False):
+        super().__init__()
+        self.indim, self.outdim = indim, outdim
+        self.num_relations, self.num_nodes, self.num_bases = num_relations, num_nodes, num_bases
+        self.input_layer, self.featureless, self.bias = input_layer, featureless, bias
+        self.weight_I = self.weight_F = self.weight_I_comp = self.weight_F_comp = self.b = None
+        S = num_relations
+        if num_bases > 0:
+            S = num_bases
+            if input_layer:
+                self.weight_I_comp = nn.Parameter(torch.empty((num_relations, num_bases)))
+            if not featureless:
+                if shared_bases_weights:
+                    self.weight_F_comp = self.weight_I_comp
+                else:
+                    self.weight_F_comp = nn.Parameter(torch.empty((num_relations, num_bases)))
+        if input_layer:
+            self.weight_I = nn.Parameter(torch.empty((S * num_nodes, outdim)))
+        if not featureless:
+            self.weight_F = nn.Parameter(torch.empty((S, indim, outdim)))
+        if bias:
+            self.b = nn.Parameter(torch.empty(outdim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for name, param in self.named_parameters():
+            if name == "b":
+                continue
+            nn.init.xavier_uniform_(param)
+        if self.bias:
+            nn.init.zeros_(self.b)
+
+    def _device(self):
+        p = self.weight_I if self.weight_I is not None else self.weight_F
+        if not p.is_cuda:
+            raise RuntimeError("mrgcn_b200.GraphConvolution has no CPU path: move the module to a CUDA device "
+                               "(task.gcn_gpu_acceleration = true)")
+        return p.device
+
+    def forward(self, X, A, A_idx=None, *, row_mask=None, relu=False):
+        """Same contract as graph.py:62: X None (featureless input layer) or (n, indim) float32; A the
+        reference's sparse COO (CPU or CUDA, int8 or float) of shape (rows, R*N) — or a prebuilt RelGraph;
+        A_idx the column subset of mini-batch mode.  `row_mask`/`relu` are optional fused extras used by RGCN."""
+        dev = self._device()
+        R = self.num_relations
+        gI = gF = None
+        wI = cI = wF = cF = None
+        if self.input_layer:
+            gI = graph_of(A, R, dev)
+            wI, cI = self.weight_I, self.weight_I_comp
+        Xd = None
+        if not (self.input_layer and self.featureless):
+            if X is None:
+                raise ValueError("X is required unless the layer is a featureless input layer")
+            Xd = X.to(dev).float()
+            wF, cF = self.weight_F, self.weight_F_comp
+            if A_idx is not None:
+                row, col, val = slice_columns_device(A, A_idx, dev)
+                gF = RelGraph.from_coo_arrays(row, col, val, A.shape[0], len(A_idx), R)
+            else:
+                gF = graph_of(A, R, dev)
+        if row_mask is not None:
+            row_mask = row_mask.to(dev).float()
+        return _LayerFn.apply(Xd, wI, cI, wF, cF, self.b, row_mask, gI, gF, self.num_bases, relu)

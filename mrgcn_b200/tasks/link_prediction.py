@@ -1,0 +1,116 @@
+"""Link-prediction hot path: DistMult scorer, in-batch negative sampling and raw/filtered ranking —
+drop-ins for the module-level functions of /root/reference/mrgcn/tasks/link_prediction.py
+(`score_distmult_bc` :645-665, negative sampling :244-268, `compute_ranks_fast` :593-643,
+`filter_scores_` :557-573, `truedicts` :576-591).  CUDA only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+
+
+class _DistMultFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, p, o, E, Rel):
+        for t, n in ((s, "s"), (p, "p"), (o, "o"), (E, "node_embeddings"), (Rel, "edge_embeddings")):
+            nv.require_cuda(t, n)
+        E, Rel = E.contiguous(), Rel.contiguous()
+        n, h = s.numel(), E.shape[1]
+        score = torch.empty(n, dtype=torch.float32, device=E.device)
+        with torch.cuda.device(E.device):
+            nv.check(nv.lib().mrgcn_distmult_fwd(nv.ptr(s), nv.ptr(p), nv.ptr(o), n, nv.ptr(E), nv.ptr(Rel), h,
+                                                 nv.ptr(score), nv.stream_ptr()), "distmult_fwd")
+        ctx.save_for_backward(s, p, o, E, Rel)
+        return score
+
+    @staticmethod
+    def backward(ctx, g):
+        s, p, o, E, Rel = ctx.saved_tensors
+        n, h = s.numel(), E.shape[1]
+        g = g.contiguous().float()
+        gE = torch.empty_like(E) if ctx.needs_input_grad[3] else None
+        gRel = torch.empty_like(Rel) if ctx.needs_input_grad[4] else None
+        ws = torch.empty(int(nv.lib().mrgcn_distmult_bwd_ws_elems(n)), dtype=torch.int32, device=E.device)
+        with torch.cuda.device(E.device):
+            nv.check(nv.lib().mrgcn_distmult_bwd(nv.ptr(s), nv.ptr(p), nv.ptr(o), n, nv.ptr(g), nv.ptr(E), nv.ptr(Rel),
+                                                 E.shape[0], Rel.shape[0], h, nv.ptr(gE), nv.ptr(gRel), nv.ptr(ws),
+                                                 nv.stream_ptr()), "distmult_bwd")
+        return None, None, None, gE, gRel
+
+
+def score_distmult_bc(data, node_embeddings, edge_embeddings):
+    """score = sum_k E[s,k] * Rel[p,k] * E[o,k] for index tensors of any common (broadcastable) shape
+    (link_prediction.py:645-665; the three matmul short-cuts of :652-663 compute the same numbers)."""
+    si, pi, oi = data
+    dev = node_embeddings.device
+    si, pi, oi = torch.broadcast_tensors(torch.as_tensor(si).to(dev).long(), torch.as_tensor(pi).to(dev).long(),
+                                         torch.as_tensor(oi).to(dev).long())
+    shape = si.shape              # every path of the reference returns the broadcast index shape
+    out = _DistMultFn.apply(si.reshape(-1).contiguous(), pi.reshape(-1).contiguous(), oi.reshape(-1).contiguous(),
+                            node_embeddings.float(), edge_embeddings.to(dev).float())
+    return out.view(shape)
+
+
+def negative_samples(batch_data, rng=np.random):
+    """link_prediction.py:244-268: corrupt floor(n/5) triples chosen without replacement, first half heads,
+    second half tails, replacements drawn from the batch's own node set; labels 1 (true) / 0 (corrupted).
+    Host NumPy RNG on purpose: same calls in the same order as the reference, so the same seed gives the
+    same corrupted triples."""
+    batch_data = np.asarray(batch_data)
+    n = batch_data.shape[0]
+    nodes = np.union1d(batch_data[:, 0], batch_data[:, 2])
+    ncorrupt = n // 5
+    pick = rng.choice(np.arange(n), ncorrupt, replace=False)
+    nhead = ncorrupt // 2
+    ntail = ncorrupt - nhead
+    corrupted = np.empty((ncorrupt, 3), dtype=int)
+    corrupted[:] = batch_data[pick]
+    corrupted[:nhead, 0] = rng.choice(nodes, nhead)
+    corrupted[-ntail:, 2] = rng.choice(nodes, ntail)
+    Y = torch.ones(n + ncorrupt, dtype=torch.float32)
+    Y[-ncorrupt:] = 0
+    return corrupted, Y
+
+
+def truedicts(facts):
+    """link_prediction.py:576-591."""
+    heads, tails = dict(), dict()
+    for s, p, o in np.asarray(facts).tolist():
+        heads.setdefault((p, o), []).append(s)
+        tails.setdefault((s, p), []).append(o)
+    return heads, tails
+
+
+def _filter_csr(data, true_dict, head):
+    ptr, idx = [0], []
+    for s, p, o in np.asarray(data).tolist():
+        idx.extend(true_dict[(p, o)] if head else true_dict[(s, p)])
+        ptr.append(len(idx))
+    return np.asarray(ptr, dtype=np.int32), np.asarray(idx if idx else [0], dtype=np.int32)
+
+
+def compute_ranks_fast(data, node_embeddings, edge_embeddings, batch_size=16, filtered=True):
+    """Ranks of every fact against all N candidate tails, then all candidate heads (loop order of
+    link_prediction.py:602).  `batch_size` (the reference's mrr_batchsize chunking, :618-625) is accepted
+    and ignored: one fused pass scores every candidate.  Returns int64 (2*facts,), 1-based."""
+    E = node_embeddings.detach().float().contiguous()
+    nv.require_cuda(E, "node_embeddings")
+    dev = E.device
+    Rel = edge_embeddings.detach().to(dev).float().contiguous()
+    data_h = torch.as_tensor(data).cpu().long()
+    facts = data_h.to(dev).contiguous()
+    F, N, h = facts.shape[0], E.shape[0], E.shape[1]
+    true_heads, true_tails = truedicts(data_h.numpy()) if filtered else (None, None)
+    out = torch.empty(2 * F, dtype=torch.int64, device=dev)
+    ws = torch.empty(max(F * N, 1), dtype=torch.float32, device=dev)
+    for k, head in enumerate((False, True)):
+        fptr = fidx = None
+        if filtered:
+            p_, i_ = _filter_csr(data_h.numpy(), true_heads if head else true_tails, head)
+            fptr, fidx = torch.from_numpy(p_).to(dev), torch.from_numpy(i_).to(dev)
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().mrgcn_distmult_rank(nv.ptr(facts), F, int(head), nv.ptr(E), nv.ptr(Rel), N, h,
+                                                  nv.ptr(fptr), nv.ptr(fidx), nv.ptr(ws), nv.ptr(out[k * F:]),
+                                                  nv.stream_ptr()), "distmult_rank")
+    return out
