@@ -103,7 +103,7 @@ int mrgcn_adjacency_from_triples(const int32_t *triples, int64_t T, int32_t N, i
 /* One R-GCN layer, forward.  Replaces GraphConvolution.forward (mrgcn/layers/graph.py:62-102)
  * plus the row-mask multiply and ReLU of RGCN._forward_full_batch (mrgcn/models/rgcn.py:78-87):
  *
- *   out[i,:] = act( mask[i] * ( b + sum_{e=(i,r,j)} val_e * ( M_I(r,j) + X[j,:] . W_F(r) ) ) )
+ *   out[i,:] = act( mask[i] * ( b + addend[i,:] + sum_{e=(i,r,j)} val_e * ( M_I(r,j) + X[j,:] . W_F(r) ) ) )
  *   M_I(r,j) = weight_I[r*NS+j,:]                       (B == 0)
  *            = sum_b comp_I[r,b] * weight_I[b*NS+j,:]   (B  > 0, graph.py:69-72)
  *   W_F(r)   = weight_F[r] or sum_b comp_F[r,b]*weight_F[b]      (graph.py:83-85)
@@ -113,12 +113,14 @@ int mrgcn_adjacency_from_triples(const int32_t *triples, int64_t T, int32_t N, i
  *     (graph.py:88-91).  Both must have the same ND.
  * weight_I [S*NS_I, out], comp_I [R,B] or NULL, X [NS_F, in] or NULL, weight_F [S, in, out],
  * comp_F [R,B] or NULL, bias [out] or NULL, row_mask [ND] or NULL, relu 0/1.
+ * addend [ND,out] or NULL: a pre-activation term computed elsewhere (the identity term of a node-partitioned
+ *   run, after its reduce-scatter).  Its gradient is `gact` of the backward call.
  * wmix: workspace [R*in*out] (only if B>0 and X given; receives W_F(r), needed by backward)
  * msg_I: workspace [E_I*out] (only if B>0 and weight_I given); msg_F: workspace [E_F*out]. */
 typedef struct mrgcn_layer_args {
   const mrgcn_graph *gI, *gF;
   int32_t in_dim, out_dim, B, relu;
-  const float *weight_I, *comp_I, *X, *weight_F, *comp_F, *bias, *row_mask;
+  const float *weight_I, *comp_I, *X, *weight_F, *comp_F, *bias, *row_mask, *addend;
   float *wmix, *msg_I, *msg_F;
   float *out; /* [ND, out] */
 } mrgcn_layer_args;

@@ -40,7 +40,7 @@ class LayerArgs(C.Structure):
         ("gI", C.POINTER(Graph)), ("gF", C.POINTER(Graph)),
         ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("B", C.c_int32), ("relu", C.c_int32),
         ("weight_I", C.c_void_p), ("comp_I", C.c_void_p), ("X", C.c_void_p), ("weight_F", C.c_void_p),
-        ("comp_F", C.c_void_p), ("bias", C.c_void_p), ("row_mask", C.c_void_p),
+        ("comp_F", C.c_void_p), ("bias", C.c_void_p), ("row_mask", C.c_void_p), ("addend", C.c_void_p),
         ("wmix", C.c_void_p), ("msg_I", C.c_void_p), ("msg_F", C.c_void_p),
         ("out", C.c_void_p),
     ]

@@ -181,7 +181,7 @@ struct AggArgs {
   const int32_t *d_src, *d_rel;
   const float *d_val;
   int64_t NSd;
-  const float *bias, *mask;
+  const float *bias, *mask, *addend;
   float *out;
   int ND, odim, relu, thresh;
 };
@@ -213,6 +213,7 @@ __device__ __forceinline__ int row_degree(const AggArgs &a, int i) {
 }
 
 __device__ __forceinline__ void agg_store(const AggArgs &a, int i, int o, float acc) {
+  if (a.addend) acc += a.addend[(size_t)i * a.odim + o];
   if (a.bias) acc += a.bias[o];
   if (a.mask) acc *= a.mask[i];
   if (a.relu) acc = fmaxf(acc, 0.f);
@@ -368,7 +369,7 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
   MRGCN_REQUIRE(!(hasI && hasF) || gI->ND == gF->ND, MRGCN_E_BADARG, "layer_fwd: graphs disagree on rows");
 
   AggArgs g{};
-  g.ND = ND; g.odim = out; g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.out = a->out;
+  g.ND = ND; g.odim = out; g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.addend = a->addend; g.out = a->out;
   const mrgcn_graph *gl = hasI ? gI : gF;  // long-row list owner
   if (hasI) {
     g.rowptr = gI->rowptr;

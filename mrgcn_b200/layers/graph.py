@@ -21,7 +21,7 @@ class _LayerFn(torch.autograd.Function):
     """out = act(mask * (b + A.W_I(mixed) + A.(X W_F(mixed))))  — graph.py:62-102 + rgcn.py:78-87."""
 
     @staticmethod
-    def forward(ctx, X, weight_I, comp_I, weight_F, comp_F, bias, row_mask, gI, gF, B, relu):
+    def forward(ctx, X, weight_I, comp_I, weight_F, comp_F, bias, row_mask, gI, gF, B, relu, addend=None):
         hasI, hasF = weight_I is not None, X is not None
         ref = weight_I if hasI else weight_F
         dev = ref.device
@@ -31,7 +31,7 @@ class _LayerFn(torch.autograd.Function):
         g0 = gI if hasI else gF
         tens = dict(X=X, weight_I=weight_I, comp_I=comp_I if (hasI and B) else None,
                     weight_F=weight_F if hasF else None, comp_F=comp_F if (hasF and B) else None,
-                    bias=bias, row_mask=row_mask)
+                    bias=bias, row_mask=row_mask, addend=addend)
         for k, t in tens.items():
             if t is not None:
                 nv.require_cuda(t, k)
@@ -56,6 +56,7 @@ class _LayerFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_fwd(C.byref(a), nv.stream_ptr()), "rgcn_layer_fwd")
         ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims = gI, gF, B, bool(relu), (in_dim, out_dim)
+        ctx.has_addend = addend is not None
         ctx.save_for_backward(tens["X"], tens["weight_I"], tens["comp_I"], tens["weight_F"], tens["comp_F"],
                               tens["bias"], tens["row_mask"], wmix, out)
         return out
@@ -107,7 +108,8 @@ class _LayerFn(torch.autograd.Function):
         b.gact, b.cbuf, b.part, b.g_wmix, b.colsum_ws = nv.ptr(gact), nv.ptr(cbuf), nv.ptr(part), nv.ptr(g_wmix), nv.ptr(colsum)
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
-        return (g_X, g_wI, g_cI, g_wF, g_cF, g_b, None, None, None, None, None)
+        g_add = gact[:g0.ND * out_dim].view(g0.ND, out_dim) if (ctx.has_addend and need[11]) else None
+        return (g_X, g_wI, g_cI, g_wF, g_cF, g_b, None, None, None, None, None, g_add)
 
 
 def slice_columns_device(A, A_idx, device):
@@ -170,7 +172,7 @@ class GraphConvolution(nn.Module):
                                "(task.gcn_gpu_acceleration = true)")
         return p.device
 
-    def forward(self, X, A, A_idx=None, *, row_mask=None, relu=False):
+    def forward(self, X, A, A_idx=None, *, row_mask=None, relu=False, addend=None):
         """Same contract as graph.py:62: X None (featureless input layer) or (n, indim) float32; A the
         reference's sparse COO (CPU or CUDA, int8 or float) of shape (rows, R*N) — or a prebuilt RelGraph;
         A_idx the column subset of mini-batch mode.  `row_mask`/`relu` are optional fused extras used by RGCN."""
@@ -194,4 +196,4 @@ class GraphConvolution(nn.Module):
                 gF = graph_of(A, R, dev)
         if row_mask is not None:
             row_mask = row_mask.to(dev).float()
-        return _LayerFn.apply(Xd, wI, cI, wF, cF, self.b, row_mask, gI, gF, self.num_bases, relu)
+        return _LayerFn.apply(Xd, wI, cI, wF, cF, self.b, row_mask, gI, gF, self.num_bases, relu, addend)
