@@ -11,11 +11,13 @@
 //                        g_X[j,k] = sum_{e: src=j} sum_o t_e[o] * W[r_e,k,o]                   (E2, per source)
 // Every reduction is a segmented sum in a fixed order: bit-reproducible, no float atomics.
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace mrgcn {
 int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
+int ident_tile_bulk(int64_t NS, int out);
 
 namespace {
 
@@ -114,18 +116,116 @@ k_ident_bwd_direct(const int32_t *__restrict__ e2_src, const int32_t *__restrict
 }
 
 // ---- identity term, B > 0, comp gradient contributions: cbuf[e2, b] = <V[b, j_e, :], t_e> ----------
-// Same tiling as k_ident_msg_fwd (V tile staged once per TJ sources); rows of cbuf are staged per warp
-// in shared memory so that the global stores are coalesced.
+// Same tiling / TMA-engine staging as k_ident_msg_fwd_bulk (rgcn_fwd.cu); one edge per lane, the lane's B
+// results are 160 contiguous bytes of cbuf (16-byte stores when B % 4 == 0).
+template <int OC, int VW>
+__device__ __forceinline__ void ident_bwd_c_tile(const float *__restrict__ Vs, size_t bstride, int RS, int B, int out, int j0,
+                                                 int e_lo, int e_hi, const int32_t *__restrict__ e2_src,
+                                                 const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val,
+                                                 const float *__restrict__ gact, float *__restrict__ cbuf) {
+  for (int e = e_lo + threadIdx.x; e < e_hi; e += kThreads) {
+    const int jl = e2_src[e] - j0;
+    const float v = e2_val[e];
+    const float *gp = gact + (size_t)e2_dst[e] * out;
+    float *cp = cbuf + (size_t)e * B;
+    for (int c0 = 0; c0 < out; c0 += OC) {
+      float t[OC];
+#pragma unroll
+      for (int o = 0; o < OC; ++o) t[o] = (c0 + o < out) ? v * gp[c0 + o] : 0.f;
+      const float *vp = Vs + (size_t)jl * RS + c0;
+      auto dot = [&](int b) {
+        const float *row = vp + (size_t)b * bstride;
+        float acc = 0.f;
+        if constexpr (VW == 4) {
+#pragma unroll
+          for (int q = 0; q < OC / 4; ++q) {
+            float4 w = reinterpret_cast<const float4 *>(row)[q];
+            acc = fmaf(w.x, t[4 * q + 0], acc); acc = fmaf(w.y, t[4 * q + 1], acc);
+            acc = fmaf(w.z, t[4 * q + 2], acc); acc = fmaf(w.w, t[4 * q + 3], acc);
+          }
+        } else if constexpr (VW == 2) {
+#pragma unroll
+          for (int q = 0; q < OC / 2; ++q) {
+            float2 w = reinterpret_cast<const float2 *>(row)[q];
+            acc = fmaf(w.x, t[2 * q + 0], acc); acc = fmaf(w.y, t[2 * q + 1], acc);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < OC; ++q)
+            if (c0 + q < out) acc = fmaf(row[q], t[q], acc);   // VW==1 rows may end at the buffer edge
+        }
+        return acc;
+      };
+      if ((B & 3) == 0) {
+#pragma unroll 2
+        for (int b = 0; b < B; b += 4) {
+          float4 c = make_float4(dot(b), dot(b + 1), dot(b + 2), dot(b + 3));
+          float4 *dst = reinterpret_cast<float4 *>(cp + b);
+          if (c0 > 0) { float4 p = *dst; c.x += p.x; c.y += p.y; c.z += p.z; c.w += p.w; }
+          *dst = c;
+        }
+      } else {
+        for (int b = 0; b < B; ++b) {
+          float c = dot(b);
+          if (c0 > 0) c += cp[b];
+          cp[b] = c;
+        }
+      }
+    }
+  }
+}
+
+template <int OC, int VW>
+__global__ void __launch_bounds__(kThreads)
+k_ident_bwd_c_bulk(const float *__restrict__ V, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_src,
+                   const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val, const float *__restrict__ gact,
+                   float *__restrict__ cbuf, int NS, int B, int out, int TJ, int S, int stage_floats, int ntiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+  float *stages = reinterpret_cast<float *>(smem_raw + 16 * ((S * 8 + 15) / 16));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t run_bytes = (uint32_t)TJ * out * 4;
+  auto issue = [&](int k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) return;
+    const int s = k % S;
+    int j0 = t * TJ;
+    if (j0 + TJ > NS) j0 = NS - TJ;
+    float *dst = stages + (size_t)s * stage_floats;
+    fence_proxy_async();
+    mbar_expect_tx(&bars[s], run_bytes * B);
+    for (int b = 0; b < B; ++b) bulk_g2s(dst + (size_t)b * TJ * out, V + ((size_t)b * NS + j0) * out, run_bytes, &bars[s]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < S - 1; ++k) issue(k);
+  for (int k = 0;; ++k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) break;
+    if (tid == 0) issue(k + S - 1);
+    int j0 = t * TJ;
+    if (j0 + TJ > NS) j0 = NS - TJ;
+    const int e_lo = colptr[j0], e_hi = colptr[j0 + TJ];
+    mbar_wait(&bars[k % S], (k / S) & 1);
+    ident_bwd_c_tile<OC, VW>(stages + (size_t)(k % S) * stage_floats, (size_t)TJ * out, out, B, out, j0, e_lo, e_hi, e2_src,
+                             e2_dst, e2_val, gact, cbuf);
+    __syncthreads();
+  }
+}
+
+// generic variant (any alignment): cooperative loads into a padded tile Vs[B][TJ][OP], pad columns zeroed
 template <int OC>
 __global__ void __launch_bounds__(kThreads)
 k_ident_bwd_c(const float *__restrict__ V, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_src,
               const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val, const float *__restrict__ gact,
-              float *__restrict__ cbuf, int NS, int B, int out, int OP, int TJ, int BS) {
+              float *__restrict__ cbuf, int NS, int B, int out, int OP, int TJ) {
   extern __shared__ __align__(16) float smem[];
-  float *Vs = smem;                               // [B][TJ][OP]
-  float *Cs_all = smem + (size_t)B * TJ * OP;     // [nwarps][32][BS]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float *Cs = Cs_all + (size_t)warp * 32 * BS;
+  float *Vs = smem;  // [B][TJ][OP]
+  const int tid = threadIdx.x;
   for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
     const int tjw = min(TJ, NS - j0);
     const int e_lo = colptr[j0], e_hi = colptr[j0 + tjw];
@@ -136,132 +236,172 @@ k_ident_bwd_c(const float *__restrict__ V, const int32_t *__restrict__ colptr, c
       int jl = x / out, o = x - jl * out;
       const float *src = V + (size_t)j0 * out + x;
       float *dst = Vs + jl * OP + o;
-#pragma unroll 8
-      for (int b = 0; b < B; ++b) dst[(size_t)b * TJ * OP] = ldg_stream(src + (size_t)b * NS * out);
+      for (int b0 = 0; b0 < B; b0 += 8) {
+        float tmp[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tmp[q] = (b0 + q < B) ? __ldg(src + (size_t)(b0 + q) * NS * out) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (b0 + q < B) dst[(size_t)(b0 + q) * TJ * OP] = tmp[q];
+      }
     }
-    // zero the padding columns (they are multiplied with t = 0 below, but must not be NaN)
-    if (OP > out)
+    if (OP > out)  // padding columns meet t = 0 but must not be NaN
       for (int x = tid; x < B * tjw * (OP - out); x += kThreads) {
         int row = x / (OP - out), o = out + x % (OP - out);
         int b = row / tjw, jl = row - b * tjw;
         Vs[((size_t)b * TJ + jl) * OP + o] = 0.f;
       }
     __syncthreads();
-    for (int eb = e_lo + warp * 32; eb < e_hi; eb += (kThreads / 32) * 32) {
-      const int e = eb + lane;
-      const bool live = e < e_hi;
-      const int jl = live ? e2_src[e] - j0 : 0;
-      const float v = live ? e2_val[e] : 0.f;
-      const float *gp = gact + (size_t)(live ? e2_dst[e] : 0) * out;
-      for (int b = 0; b < B; ++b) Cs[lane * BS + b] = 0.f;
-      for (int c0 = 0; c0 < OP; c0 += OC) {
-        float t[OC];
-#pragma unroll
-        for (int o = 0; o < OC; ++o) t[o] = (live && c0 + o < out) ? v * gp[c0 + o] : 0.f;
-        const float *vp = Vs + jl * OP + c0;
-        for (int b = 0; b < B; ++b) {
-          const float4 *v4 = reinterpret_cast<const float4 *>(vp + (size_t)b * TJ * OP);
-          float acc = 0.f;
-#pragma unroll
-          for (int q = 0; q < OC / 4; ++q) {
-            float4 w = v4[q];
-            acc = fmaf(w.x, t[4 * q + 0], acc);
-            acc = fmaf(w.y, t[4 * q + 1], acc);
-            acc = fmaf(w.z, t[4 * q + 2], acc);
-            acc = fmaf(w.w, t[4 * q + 3], acc);
-          }
-          Cs[lane * BS + b] += acc;
-        }
-      }
-      __syncwarp();
-      // coalesced write-out of the 32 x B block (rows are consecutive in cbuf)
-      const int nlive = min(32, e_hi - eb);
-      float *cp = cbuf + (size_t)eb * B;
-      for (int x = lane; x < nlive * B; x += 32) {
-        int row = x / B, b = x - row * B;
-        cp[x] = Cs[row * BS + b];
-      }
-      __syncwarp();
-    }
+    ident_bwd_c_tile<OC, 4>(Vs, (size_t)TJ * OP, OP, B, out, j0, e_lo, e_hi, e2_src, e2_dst, e2_val, gact, cbuf);
   }
 }
 
 // ---- identity term, B > 0, basis gradient: g_weight_I[b, j, o] = sum_{e: src=j} comp[r_e,b] * t_e[o] ----
-// One thread per output column x = (j - j0)*out + o of a tile of TJ sources; BC bases at a time in registers.
-// Stores are coalesced across the tile (consecutive x for a fixed basis).  Sources with degree > thresh are
-// left to k_ident_bwd_w_long.
-constexpr int BC = 8;
+// A CTA walks tiles of TJ sources (TJ*out <= 256).  Per tile: (1) every thread stages t_e = val_e*gact[dst_e,:]
+// of one edge into shared memory (all gathers independent -> deep memory-level parallelism), (2) one thread per
+// output column x = (j - j0)*out + o accumulates ALL bases in registers over the source's edges out of shared
+// memory, (3) stores are coalesced across the tile (consecutive x for a fixed basis).
+// Sources with more than `thresh` edges are left to k_ident_bwd_w_long.
+// edges staged per round: as many as fit ~48 KB, at most 512
+static int pick_ec(int out) {
+  int ec = (48 * 1024) / (4 * (out + 1));
+  ec = ec > 512 ? 512 : ec;
+  return ec < 32 ? 32 : (ec / 32) * 32;
+}
+template <int BT>
 __global__ void __launch_bounds__(kThreads)
 k_ident_bwd_w(const float *__restrict__ comp, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
               const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
-              float *__restrict__ gW, int NS, int R, int B, int out, int TJ, int CS, int thresh) {
-  extern __shared__ __align__(16) float comp_s[];  // [R][CS], CS = B rounded up to BC, zero padded
+              float *__restrict__ gW, int NS, int R, int B, int out, int TJ, int thresh, int EC) {
+  extern __shared__ __align__(16) float smem[];
+  float *comp_s = smem;                 // [R][BT], zero padded
+  float *Ts = smem + (size_t)R * BT;    // [EC][out]
+  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EC * out);  // [EC]
   const int tid = threadIdx.x;
-  for (int x = tid; x < R * CS; x += kThreads) {
-    int r = x / CS, b = x - r * CS;
+  for (int x = tid; x < R * BT; x += kThreads) {
+    int r = x / BT, b = x - r * BT;
     comp_s[x] = b < B ? __ldg(comp + (size_t)r * B + b) : 0.f;
   }
-  __syncthreads();
   for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
     const int tjw = min(TJ, NS - j0);
-    for (int x = tid; x < tjw * out; x += kThreads) {
-      const int jl = x / out, o = x - jl * out;
-      const int e_lo = colptr[j0 + jl], e_hi = colptr[j0 + jl + 1];
-      const bool skip = thresh > 0 && e_hi - e_lo > thresh;
-      for (int b0 = 0; b0 < B; b0 += BC) {
-        float acc[BC];
+    const int t_lo = colptr[j0], t_hi = colptr[j0 + tjw];
+    const bool mine = tid < tjw * out;
+    const int jl = mine ? tid / out : 0, o = tid - jl * out;
+    int s_lo = 0, s_hi = 0;
+    if (mine) {
+      s_lo = colptr[j0 + jl];
+      s_hi = colptr[j0 + jl + 1];
+      if (thresh > 0 && s_hi - s_lo > thresh) s_hi = s_lo;  // hub: other kernel
+    }
+    float acc[BT];
 #pragma unroll
-        for (int q = 0; q < BC; ++q) acc[q] = 0.f;
-        if (!skip)
-          for (int e = e_lo; e < e_hi; ++e) {
-            const float t = e2_val[e] * gact[(size_t)e2_dst[e] * out + o];
-            const float4 *c4 = reinterpret_cast<const float4 *>(comp_s + (size_t)e2_rel[e] * CS + b0);
+    for (int q = 0; q < BT; ++q) acc[q] = 0.f;
+    for (int c_lo = t_lo; c_lo < t_hi; c_lo += EC) {
+      const int c_hi = min(t_hi, c_lo + EC);
+      __syncthreads();
+      for (int el = tid; el < c_hi - c_lo; el += kThreads) {
+        const int e = c_lo + el;
+        const float v = e2_val[e];
+        const float *gp = gact + (size_t)e2_dst[e] * out;
+        Rs[el] = e2_rel[e];
+        for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
+      }
+      __syncthreads();
+      const int lo = max(s_lo, c_lo), hi = min(s_hi, c_hi);
+      for (int e = lo; e < hi; ++e) {
+        const float t = Ts[(e - c_lo) * out + o];
+        const float4 *c4 = reinterpret_cast<const float4 *>(comp_s + (size_t)Rs[e - c_lo] * BT);
 #pragma unroll
-            for (int q = 0; q < BC / 4; ++q) {
-              float4 c = c4[q];
-              acc[4 * q + 0] = fmaf(c.x, t, acc[4 * q + 0]);
-              acc[4 * q + 1] = fmaf(c.y, t, acc[4 * q + 1]);
-              acc[4 * q + 2] = fmaf(c.z, t, acc[4 * q + 2]);
-              acc[4 * q + 3] = fmaf(c.w, t, acc[4 * q + 3]);
-            }
-          }
-        if (!skip) {
-#pragma unroll
-          for (int q = 0; q < BC; ++q)
-            if (b0 + q < B) gW[((size_t)(b0 + q) * NS + j0) * out + x] = acc[q];
+        for (int q = 0; q < BT / 4; ++q) {
+          float4 c = c4[q];
+          acc[4 * q + 0] = fmaf(c.x, t, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(c.y, t, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(c.z, t, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(c.w, t, acc[4 * q + 3]);
         }
       }
+    }
+    if (mine && !(thresh > 0 && colptr[j0 + jl + 1] - colptr[j0 + jl] > thresh)) {
+#pragma unroll
+      for (int q = 0; q < BT; ++q)
+        if (q < B) gW[((size_t)q * NS + j0) * out + tid] = acc[q];
     }
   }
 }
 
-// hubs: one CTA per long source; edge slots strided over the source's edges, fixed-order tree over slots
+// generic fallback (B > 64 or out > 256): one thread per output column, BC bases at a time, no staging
+constexpr int BC = 8;
+__global__ void __launch_bounds__(kThreads)
+k_ident_bwd_w_generic(const float *__restrict__ comp, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
+                      const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
+                      float *__restrict__ gW, int64_t NS, int B, int out, int thresh) {
+  const int64_t x = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (x >= NS * out) return;
+  const int64_t j = x / out;
+  const int o = (int)(x - j * out);
+  const int e_lo = colptr[j], e_hi = colptr[j + 1];
+  if (thresh > 0 && e_hi - e_lo > thresh) return;
+  for (int b0 = 0; b0 < B; b0 += BC) {
+    float acc[BC];
+#pragma unroll
+    for (int q = 0; q < BC; ++q) acc[q] = 0.f;
+    for (int e = e_lo; e < e_hi; ++e) {
+      const float t = e2_val[e] * gact[(size_t)e2_dst[e] * out + o];
+      const float *cr = comp + (size_t)e2_rel[e] * B + b0;
+#pragma unroll
+      for (int q = 0; q < BC; ++q)
+        if (b0 + q < B) acc[q] = fmaf(__ldg(cr + q), t, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < BC; ++q)
+      if (b0 + q < B) gW[((size_t)(b0 + q) * NS + j) * out + o] = acc[q];
+  }
+}
+
+// hubs: one CTA per long source.  Rounds of EC edges are staged like above; thread p owns the (basis, o) pairs
+// p, p + 256, ... and walks the staged edges sequentially (fixed order).
 __global__ void __launch_bounds__(kThreads)
 k_ident_bwd_w_long(const float *__restrict__ comp, const int32_t *__restrict__ long_cols,
                    const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
                    const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
-                   const float *__restrict__ gact, float *__restrict__ gW, int NS, int B, int out) {
-  __shared__ float red[kThreads];
+                   const float *__restrict__ gact, float *__restrict__ gW, int64_t NS, int B, int out, int EL) {
+  extern __shared__ __align__(16) float smem[];
+  float *Ts = smem;                                          // [EL][out]
+  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EL * out);  // [EL]
   const int j = long_cols[blockIdx.x];
   const int e_lo = colptr[j], e_hi = colptr[j + 1];
-  const int oc = min(out, kThreads), nslots = kThreads / oc;
-  const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
-  for (int o0 = 0; o0 < out; o0 += oc) {
-    const int o = o0 + ol;
-    for (int b = 0; b < B; ++b) {
-      float acc = 0.f;
-      if (slot < nslots && o < out)
-        for (int e = e_lo + slot; e < e_hi; e += nslots)
-          acc = fmaf(__ldg(comp + (size_t)e2_rel[e] * B + b), e2_val[e] * gact[(size_t)e2_dst[e] * out + o], acc);
-      if (slot < nslots) red[slot * oc + ol] = acc;
-      __syncthreads();
-      for (int s = 1; s < nslots; s <<= 1) {
-        if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
-        __syncthreads();
-      }
-      if (slot == 0 && o < out) gW[((size_t)b * NS + j) * out + o] = red[ol];
-      __syncthreads();
+  const int tid = threadIdx.x;
+  const int npairs = B * out;
+  for (int p0 = 0; p0 < npairs; p0 += 4 * kThreads) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int pb[4], po[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = p0 + q * kThreads + tid;
+      pb[q] = p < npairs ? p / out : -1;
+      po[q] = p < npairs ? p - pb[q] * out : 0;
     }
+    for (int c_lo = e_lo; c_lo < e_hi; c_lo += EL) {
+      const int n = min(EL, e_hi - c_lo);
+      __syncthreads();
+      for (int el = tid; el < n; el += kThreads) {
+        const int e = c_lo + el;
+        const float v = e2_val[e];
+        const float *gp = gact + (size_t)e2_dst[e] * out;
+        Rs[el] = e2_rel[e];
+        for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
+      }
+      __syncthreads();
+      for (int el = 0; el < n; ++el) {
+        const float *cr = comp + (size_t)Rs[el] * B;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (pb[q] >= 0) acc[q] = fmaf(__ldg(cr + pb[q]), Ts[el * out + po[q]], acc[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (pb[q] >= 0) gW[((size_t)pb[q] * NS + j) * out + po[q]] = acc[q];
   }
 }
 
@@ -371,26 +511,62 @@ k_basis_mix_bwd_c(const float *__restrict__ V, const float *__restrict__ gW, flo
 }
 
 // ---- input gradient: g_X[j,k] = sum_{e: src=j} val_e * sum_o gact[dst_e,o] * W[r_e,k,o] -------------
-// one thread per (j,k); hubs handled by the _long variant.
+// Tiles of TJ sources (TJ*in <= 256): t_e staged per round in shared memory (independent gathers), one thread per
+// (j,k) walks the source's staged edges; W rows come through L1/L2 (R*in*out floats, hot relations stay in L1).
 __global__ void __launch_bounds__(kThreads)
 k_feat_bwd_x(const float *__restrict__ W, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
              const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
-             float *__restrict__ gX, int64_t NS, int in, int out, int thresh) {
-  const int64_t x = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (x >= NS * in) return;
-  const int64_t j = x / in;
-  const int k = (int)(x - j * in);
-  const int e_lo = colptr[j], e_hi = colptr[j + 1];
-  if (thresh > 0 && e_hi - e_lo > thresh) return;
-  float acc = 0.f;
-  for (int e = e_lo; e < e_hi; ++e) {
-    const float *gp = gact + (size_t)e2_dst[e] * out;
-    const float *wp = W + ((size_t)e2_rel[e] * in + k) * out;
-    float d = 0.f;
-    for (int o = 0; o < out; ++o) d = fmaf(gp[o], __ldg(wp + o), d);
-    acc = fmaf(e2_val[e], d, acc);
+             float *__restrict__ gX, int NS, int in, int out, int TJ, int thresh, int EC) {
+  extern __shared__ __align__(16) float smem[];
+  float *Ts = smem;                                          // [EC][out]
+  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EC * out);  // [EC]
+  const int tid = threadIdx.x;
+  for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
+    const int tjw = min(TJ, NS - j0);
+    const int t_lo = colptr[j0], t_hi = colptr[j0 + tjw];
+    for (int k0 = 0; k0 < in; k0 += kThreads) {   // in > 256 only: TJ == 1, columns in rounds
+      const int cols = TJ == 1 ? min(kThreads, in - k0) : tjw * in;
+      const bool mine = tid < cols;
+      const int jl = (mine && TJ > 1) ? tid / in : 0;
+      const int k = TJ > 1 ? tid - jl * in : k0 + tid;
+      int s_lo = 0, s_hi = 0;
+      bool hub = false;
+      if (mine) {
+        s_lo = colptr[j0 + jl];
+        s_hi = colptr[j0 + jl + 1];
+        hub = thresh > 0 && s_hi - s_lo > thresh;
+        if (hub) s_hi = s_lo;
+      }
+      float acc = 0.f;
+      for (int c_lo = t_lo; c_lo < t_hi; c_lo += EC) {
+        const int c_hi = min(t_hi, c_lo + EC);
+        __syncthreads();
+        for (int el = tid; el < c_hi - c_lo; el += kThreads) {
+          const int e = c_lo + el;
+          const float v = e2_val[e];
+          const float *gp = gact + (size_t)e2_dst[e] * out;
+          Rs[el] = e2_rel[e];
+          for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
+        }
+        __syncthreads();
+        const int lo = max(s_lo, c_lo), hi = min(s_hi, c_hi);
+        for (int e = lo; e < hi; ++e) {
+          const float *tp = Ts + (e - c_lo) * out;
+          const float *wp = W + ((size_t)Rs[e - c_lo] * in + k) * out;
+          float d0 = 0.f, d1 = 0.f;
+          int q = 0;
+          for (; q + 1 < out; q += 2) {
+            d0 = fmaf(tp[q], __ldg(wp + q), d0);
+            d1 = fmaf(tp[q + 1], __ldg(wp + q + 1), d1);
+          }
+          if (q < out) d0 = fmaf(tp[q], __ldg(wp + q), d0);
+          acc += d0 + d1;
+        }
+      }
+      if (mine && !hub) gX[(size_t)(j0 + jl) * in + k] = acc;
+      if (TJ > 1) break;
+    }
   }
-  gX[x] = acc;
 }
 __global__ void __launch_bounds__(kThreads)
 k_feat_bwd_x_long(const float *__restrict__ W, const int32_t *__restrict__ long_cols, const int32_t *__restrict__ colptr,
@@ -472,56 +648,128 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       }
     } else {
       const int OC = pick_oc(out);
-      const int OP = (int)cdiv(out, OC) * OC;
-      const int TJ = ident_tile(B, out, OP);
+      const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
       {  // basis gradient
-        const int CS = (int)cdiv(B, BC) * BC;
-        size_t smem = (size_t)gI->R * CS * 4;
-        MRGCN_REQUIRE(smem <= 200 * 1024, MRGCN_E_NOTSUP, "ident_bwd_w: R*B too large for shared memory");
-        if (int rc = set_smem(k_ident_bwd_w, smem)) return rc;
-        const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
-        unsigned grid = persistent_grid(k_ident_bwd_w, kThreads, smem, cdiv(NS, TJ));
-        MRGCN_PROF("ident_bwd_w");
-  k_ident_bwd_w<<<grid, kThreads, smem, st>>>(f.comp_I, gI->colptr, gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact,
-                                                    a->g_weight_I, (int)NS, gI->R, B, out, TJ, CS, thresh);
-        MRGCN_LAUNCH_CHECK();
+        if (B <= 64 && out <= 256) {
+          const int BT = (int)cdiv(B, 8) * 8;
+          const int TJ = 256 / out;
+          const int EC = pick_ec(out);
+          size_t smem = ((size_t)gI->R * BT + (size_t)EC * out + EC) * 4;
+          MRGCN_REQUIRE(smem <= 200 * 1024, MRGCN_E_NOTSUP, "ident_bwd_w: R*B too large for shared memory");
+          unsigned grid = 0;
+          MRGCN_PROF("ident_bwd_w");
+#define LAUNCH(BTV)                                                                                              \
+  do {                                                                                                           \
+    if (int rc = set_smem(k_ident_bwd_w<BTV>, smem)) return rc;                                                  \
+    grid = persistent_grid(k_ident_bwd_w<BTV>, kThreads, smem, cdiv(NS, TJ));                                    \
+    k_ident_bwd_w<BTV><<<grid, kThreads, smem, st>>>(f.comp_I, gI->colptr, gI->e2_dst, gI->e2_rel, gI->e2_val,   \
+                                                     a->gact, a->g_weight_I, (int)NS, gI->R, B, out, TJ, thresh, EC); \
+  } while (0)
+          switch (BT) {
+            case 8: LAUNCH(8); break;
+            case 16: LAUNCH(16); break;
+            case 24: LAUNCH(24); break;
+            case 32: LAUNCH(32); break;
+            case 40: LAUNCH(40); break;
+            case 48: LAUNCH(48); break;
+            case 56: LAUNCH(56); break;
+            default: LAUNCH(64); break;
+          }
+#undef LAUNCH
+          MRGCN_LAUNCH_CHECK();
+        } else {
+          MRGCN_PROF("ident_bwd_w");
+          k_ident_bwd_w_generic<<<(unsigned)cdiv(NS * out, kThreads), kThreads, 0, st>>>(
+              f.comp_I, gI->colptr, gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact, a->g_weight_I, NS, B, out, thresh);
+          MRGCN_LAUNCH_CHECK();
+        }
         if (gI->n_long_cols > 0) {
+          int EL = 1024;
+          while (EL > 32 && ((size_t)EL * out + EL) * 4 > 96 * 1024) EL >>= 1;
+          size_t smem = ((size_t)EL * out + EL) * 4;
+          if (int rc = set_smem(k_ident_bwd_w_long, smem)) return rc;
           MRGCN_PROF("ident_bwd_w_long");
-  k_ident_bwd_w_long<<<(unsigned)gI->n_long_cols, kThreads, 0, st>>>(f.comp_I, gI->long_cols, gI->colptr,
-                                                                             gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact,
-                                                                             a->g_weight_I, (int)NS, B, out);
+          k_ident_bwd_w_long<<<(unsigned)gI->n_long_cols, kThreads, smem, st>>>(f.comp_I, gI->long_cols, gI->colptr,
+                                                                                gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact,
+                                                                                a->g_weight_I, NS, B, out, EL);
           MRGCN_LAUNCH_CHECK();
         }
       }
       if (a->g_comp_I) {
         MRGCN_REQUIRE(a->cbuf && a->part, MRGCN_E_BADARG, "layer_bwd: cbuf/part missing");
         if (gI->E > 0) {
-          const int BS = B | 1;
-          size_t smem = ((size_t)B * TJ * OP + (size_t)(kThreads / 32) * 32 * BS) * 4;
-          MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "ident_bwd_c: B*out too large for shared memory");
           unsigned grid = 0;
+          const int TJb = ident_tile_bulk(NS, out);
+          int S = 0;
+          size_t smem = 0;
+          int stage_floats = 0;
+          if (TJb > 0) {
+            stage_floats = ((B * TJb * out + 3) & ~3) + 16;
+            for (S = 4; S >= 2; --S) {
+              smem = 16 * ((S * 8 + 15) / 16) + (size_t)S * stage_floats * 4;
+              if (smem <= 100 * 1024) break;
+            }
+            if (S < 2)
+              for (S = 4; S >= 2; --S) {
+                smem = 16 * ((S * 8 + 15) / 16) + (size_t)S * stage_floats * 4;
+                if (smem <= 200 * 1024) break;
+              }
+          }
+          if (TJb > 0 && S >= 2) {
+            const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
+            const int ntiles = (int)cdiv(NS, TJb);
+            MRGCN_PROF("ident_bwd_c");
+#define LAUNCH(OCV, VWV)                                                                                          \
+  do {                                                                                                            \
+    if (int rc = set_smem(k_ident_bwd_c_bulk<OCV, VWV>, smem)) return rc;                                         \
+    grid = persistent_grid(k_ident_bwd_c_bulk<OCV, VWV>, kThreads, smem, ntiles);                                 \
+    k_ident_bwd_c_bulk<OCV, VWV><<<grid, kThreads, smem, st>>>(f.weight_I, gI->colptr, gI->e2_src, gI->e2_dst,    \
+                                                               gI->e2_val, a->gact, a->cbuf, (int)NS, B, out, TJb, \
+                                                               S, stage_floats, ntiles);                          \
+  } while (0)
+#define LAUNCH_VW(OCV)                \
+  do {                                \
+    if (VW == 4) LAUNCH(OCV, 4);      \
+    else if (VW == 2) LAUNCH(OCV, 2); \
+    else LAUNCH(OCV, 1);              \
+  } while (0)
+            switch (OC) {
+              case 4: LAUNCH_VW(4); break;
+              case 8: LAUNCH_VW(8); break;
+              case 12: LAUNCH_VW(12); break;
+              default: LAUNCH_VW(16); break;
+            }
+#undef LAUNCH_VW
+#undef LAUNCH
+            MRGCN_LAUNCH_CHECK();
+          } else {
+            const int OP = (int)cdiv(out, OC) * OC;
+            const int TJ = ident_tile(B, out, OP);
+            smem = (size_t)B * TJ * OP * 4;
+            MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "ident_bwd_c: B*out too large for shared memory");
+            MRGCN_PROF("ident_bwd_c");
 #define LAUNCH(OCV)                                                                                              \
   do {                                                                                                           \
     if (int rc = set_smem(k_ident_bwd_c<OCV>, smem)) return rc;                                                  \
     grid = persistent_grid(k_ident_bwd_c<OCV>, kThreads, smem, cdiv(NS, TJ));                                    \
     k_ident_bwd_c<OCV><<<grid, kThreads, smem, st>>>(f.weight_I, gI->colptr, gI->e2_src, gI->e2_dst, gI->e2_val, \
-                                                     a->gact, a->cbuf, (int)NS, B, out, OP, TJ, BS);             \
+                                                     a->gact, a->cbuf, (int)NS, B, out, OP, TJ);                 \
   } while (0)
-          MRGCN_PROF("ident_bwd_c");
-  switch (OC) {
-            case 4: LAUNCH(4); break;
-            case 8: LAUNCH(8); break;
-            case 12: LAUNCH(12); break;
-            default: LAUNCH(16); break;
-          }
+            switch (OC) {
+              case 4: LAUNCH(4); break;
+              case 8: LAUNCH(8); break;
+              case 12: LAUNCH(12); break;
+              default: LAUNCH(16); break;
+            }
 #undef LAUNCH
-          MRGCN_LAUNCH_CHECK();
+            MRGCN_LAUNCH_CHECK();
+          }
           MRGCN_PROF("comp_chunk_reduce");
-  k_comp_chunk_reduce<<<(unsigned)gI->n_chunks, kThreads, 0, st>>>(a->cbuf, gI->chunk_ptr, gI->e3_to_e2, a->part, B);
+          k_comp_chunk_reduce<<<(unsigned)gI->n_chunks, kThreads, 0, st>>>(a->cbuf, gI->chunk_ptr, gI->e3_to_e2, a->part, B);
           MRGCN_LAUNCH_CHECK();
         }
         MRGCN_PROF("comp_reduce");
-  k_seq_reduce<<<dim3((unsigned)cdiv(B, 128), (unsigned)gI->R), 128, 0, st>>>(a->part, gI->rel_chunk_ptr,
+        k_seq_reduce<<<dim3((unsigned)cdiv(B, 128), (unsigned)gI->R), 128, 0, st>>>(a->part, gI->rel_chunk_ptr,
                                                                                     gI->n_chunks, B, a->g_comp_I);
         MRGCN_LAUNCH_CHECK();
       }
@@ -569,13 +817,19 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       const int64_t NS = gF->NS;
       const int thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
       if (NS > 0) {
+        const int TJ = in >= kThreads ? 1 : kThreads / in;
+        const int EC = pick_ec(out);
+        size_t smem = ((size_t)EC * out + EC) * 4;
+        MRGCN_REQUIRE(smem <= 200 * 1024, MRGCN_E_NOTSUP, "feat_bwd_x: out too large for shared memory");
+        if (int rc = set_smem(k_feat_bwd_x, smem)) return rc;
+        unsigned grid = persistent_grid(k_feat_bwd_x, kThreads, smem, cdiv(NS, TJ));
         MRGCN_PROF("feat_bwd_x");
-  k_feat_bwd_x<<<(unsigned)cdiv(NS * in, kThreads), kThreads, 0, st>>>(W, gF->colptr, gF->e2_dst, gF->e2_rel, gF->e2_val,
-                                                                             a->gact, a->g_X, NS, in, out, thresh);
+        k_feat_bwd_x<<<grid, kThreads, smem, st>>>(W, gF->colptr, gF->e2_dst, gF->e2_rel, gF->e2_val, a->gact, a->g_X,
+                                                   (int)NS, in, out, TJ, thresh, EC);
         MRGCN_LAUNCH_CHECK();
         if (gF->n_long_cols > 0) {
           MRGCN_PROF("feat_bwd_x_long");
-  k_feat_bwd_x_long<<<(unsigned)gF->n_long_cols, kThreads, 0, st>>>(W, gF->long_cols, gF->colptr, gF->e2_dst, gF->e2_rel,
+          k_feat_bwd_x_long<<<(unsigned)gF->n_long_cols, kThreads, 0, st>>>(W, gF->long_cols, gF->colptr, gF->e2_dst, gF->e2_rel,
                                                                             gF->e2_val, a->gact, a->g_X, in, out);
           MRGCN_LAUNCH_CHECK();
         }

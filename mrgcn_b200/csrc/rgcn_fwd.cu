@@ -13,6 +13,7 @@
 //                        row (+ the direct weight_I row gather when B == 0) fused with bias, row mask, ReLU.
 // All passes are HBM/L2-bound gathers; there is no float atomic anywhere.
 #include "common.cuh"
+#include "pipeline.cuh"
 
 namespace mrgcn {
 namespace {
@@ -34,8 +35,121 @@ __global__ void k_basis_mix_fwd(const float *__restrict__ comp, const float *__r
 // ------------------------------------------------------------------------------------------------
 // Identity term with basis decomposition (graph.py:69-75), source-major.
 //   msg[e2, :] = val_e * sum_b comp[r_e, b] * V[b, j_e, :]
-// smem: comp_s[R][CS] (CS odd -> lanes with different relations hit different banks) then
-//       Vs[B][TJ][OP] (OP = out rounded up to a multiple of OC; rows 16B aligned for LDS.128).
+// A CTA walks tiles of TJ consecutive sources.  The tile V[:, j0:j0+TJ, :] is B contiguous runs of TJ*out
+// floats; it is read from HBM exactly once and mixed per edge out of shared memory.
+
+// acc[0..OC) += c * row[0..OC) for every basis; row stride between bases = bstride floats
+template <int OC, int VW>
+__device__ __forceinline__ void mix_bases(const float *__restrict__ vp, size_t bstride, const float *__restrict__ cr,
+                                          int B, float (&acc)[OC]) {
+#pragma unroll 4
+  for (int b = 0; b < B; ++b) {
+    const float c = cr[b];
+    const float *row = vp + (size_t)b * bstride;
+    if constexpr (VW == 4) {
+#pragma unroll
+      for (int q = 0; q < OC / 4; ++q) {
+        float4 t = reinterpret_cast<const float4 *>(row)[q];
+        acc[4 * q + 0] = fmaf(c, t.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(c, t.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(c, t.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(c, t.w, acc[4 * q + 3]);
+      }
+    } else if constexpr (VW == 2) {
+#pragma unroll
+      for (int q = 0; q < OC / 2; ++q) {
+        float2 t = reinterpret_cast<const float2 *>(row)[q];
+        acc[2 * q + 0] = fmaf(c, t.x, acc[2 * q + 0]);
+        acc[2 * q + 1] = fmaf(c, t.y, acc[2 * q + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < OC; ++q) acc[q] = fmaf(c, row[q], acc[q]);
+    }
+  }
+}
+
+// per-edge work of one staged tile: RS = row stride (floats) of a (basis, source) row in the tile
+template <int OC, int VW>
+__device__ __forceinline__ void ident_msg_tile(const float *__restrict__ Vs, size_t bstride, int RS,
+                                               const float *__restrict__ comp_s, int CS, const float *__restrict__ comp,
+                                               int B, int out, int j0, int e_lo, int e_hi,
+                                               const int32_t *__restrict__ e2_src, const int32_t *__restrict__ e2_rel,
+                                               const float *__restrict__ e2_val, float *__restrict__ msg) {
+  for (int e = e_lo + threadIdx.x; e < e_hi; e += kThreads) {
+    const int jl = e2_src[e] - j0, r = e2_rel[e];
+    const float v = e2_val[e];
+    const float *cr = comp_s ? comp_s + r * CS : comp + (size_t)r * B;
+    for (int c0 = 0; c0 < out; c0 += OC) {
+      float acc[OC];
+#pragma unroll
+      for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+      mix_bases<OC, VW>(Vs + (size_t)jl * RS + c0, bstride, cr, B, acc);
+      float *mp = msg + (size_t)e * out + c0;
+#pragma unroll
+      for (int o = 0; o < OC; ++o)
+        if (c0 + o < out) mp[o] = v * acc[o];
+    }
+  }
+}
+
+__device__ __forceinline__ void load_comp_smem(float *comp_s, const float *__restrict__ comp, int R, int B, int CS) {
+  for (int r = threadIdx.x / 32; r < R; r += kThreads / 32)
+    for (int b = threadIdx.x & 31; b < B; b += 32) comp_s[r * CS + b] = __ldg(comp + (size_t)r * B + b);
+}
+
+// (a) TMA-engine variant: every basis run of the tile is one cp.async.bulk into a ring of S stages, completion on
+//     an mbarrier per stage; thread 0 is the producer, all threads consume.  Needs 16-byte aligned runs:
+//     (NS*out) % 4 == 0, (TJ*out) % 4 == 0, NS >= TJ.  The last tile is shifted back to NS-TJ so that every tile
+//     is full; the sources it shares with its predecessor produce identical messages twice.
+template <int OC, int VW>
+__global__ void __launch_bounds__(kThreads)
+k_ident_msg_fwd_bulk(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
+                     const int32_t *__restrict__ e2_src, const int32_t *__restrict__ e2_rel,
+                     const float *__restrict__ e2_val, float *__restrict__ msg, int NS, int R, int B, int out, int TJ,
+                     int CS, int comp_smem, int S, int stage_floats, int ntiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+  float *comp_s = reinterpret_cast<float *>(smem_raw + 16 * ((S * 8 + 15) / 16));
+  float *stages = comp_s + (comp_smem ? ((R * CS + 3) & ~3) : 0);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  if (comp_smem) load_comp_smem(comp_s, comp, R, B, CS);
+  __syncthreads();
+  const uint32_t run_bytes = (uint32_t)TJ * out * 4;
+  auto issue = [&](int k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) return;
+    const int s = k % S;
+    int j0 = t * TJ;
+    if (j0 + TJ > NS) j0 = NS - TJ;
+    float *dst = stages + (size_t)s * stage_floats;
+    fence_proxy_async();
+    mbar_expect_tx(&bars[s], run_bytes * B);
+    for (int b = 0; b < B; ++b)
+      bulk_g2s(dst + (size_t)b * TJ * out, V + ((size_t)b * NS + j0) * out, run_bytes, &bars[s]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < S - 1; ++k) issue(k);
+  for (int k = 0;; ++k) {
+    const int t = blockIdx.x + k * gridDim.x;
+    if (t >= ntiles) break;
+    if (tid == 0) issue(k + S - 1);
+    int j0 = t * TJ;
+    if (j0 + TJ > NS) j0 = NS - TJ;
+    const int e_lo = colptr[j0], e_hi = colptr[j0 + TJ];
+    mbar_wait(&bars[k % S], (k / S) & 1);
+    ident_msg_tile<OC, VW>(stages + (size_t)(k % S) * stage_floats, (size_t)TJ * out, out, comp_smem ? comp_s : nullptr, CS,
+                           comp, B, out, j0, e_lo, e_hi, e2_src, e2_rel, e2_val, msg);
+    __syncthreads();  // stage (k % S) may be refilled by the producer in the next iteration
+  }
+}
+
+// (b) generic variant (any alignment): cooperative coalesced loads into a padded tile.
+//     smem: comp_s[R][CS] then Vs[B][TJ][OP] (OP = out rounded up to a multiple of OC; rows 16B aligned).
 template <int OC>
 __global__ void __launch_bounds__(kThreads)
 k_ident_msg_fwd(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
@@ -46,53 +160,29 @@ k_ident_msg_fwd(const float *__restrict__ V, const float *__restrict__ comp, con
   float *comp_s = smem;
   float *Vs = smem + (comp_smem ? ((R * CS + 3) & ~3) : 0);
   const int tid = threadIdx.x;
-  if (comp_smem) {
-    for (int r = tid / 32; r < R; r += kThreads / 32)
-      for (int b = tid & 31; b < B; b += 32) comp_s[r * CS + b] = __ldg(comp + (size_t)r * B + b);
-  }
-  // persistent: a CTA walks tiles of TJ consecutive sources (comp stays resident)
+  if (comp_smem) load_comp_smem(comp_s, comp, R, B, CS);
   for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
     const int tjw = min(TJ, NS - j0);
     const int e_lo = colptr[j0], e_hi = colptr[j0 + tjw];
     if (e_lo == e_hi) continue;
     __syncthreads();  // previous tile fully consumed (and comp_s visible)
-    // stage the tile: for every basis one contiguous run of tjw*out floats
     const int run = tjw * out;
     for (int x = tid; x < run; x += kThreads) {
       int jl = x / out, o = x - jl * out;
       const float *src = V + (size_t)j0 * out + x;
       float *dst = Vs + jl * OP + o;
-#pragma unroll 8
-      for (int b = 0; b < B; ++b) dst[(size_t)b * TJ * OP] = ldg_stream(src + (size_t)b * NS * out);
-    }
-    __syncthreads();
-    for (int e = e_lo + tid; e < e_hi; e += kThreads) {
-      const int jl = e2_src[e] - j0, r = e2_rel[e];
-      const float v = e2_val[e];
-      const float *cr = comp_smem ? comp_s + r * CS : comp + (size_t)r * B;
-      for (int c0 = 0; c0 < OP; c0 += OC) {
-        float acc[OC];
+      for (int b0 = 0; b0 < B; b0 += 8) {  // 8 independent loads in flight per thread
+        float tmp[8];
 #pragma unroll
-        for (int o = 0; o < OC; ++o) acc[o] = 0.f;
-        const float *vp = Vs + jl * OP + c0;
-        for (int b = 0; b < B; ++b) {
-          const float c = cr[b];
-          const float4 *v4 = reinterpret_cast<const float4 *>(vp + (size_t)b * TJ * OP);
+        for (int q = 0; q < 8; ++q) tmp[q] = (b0 + q < B) ? __ldg(src + (size_t)(b0 + q) * NS * out) : 0.f;
 #pragma unroll
-          for (int q = 0; q < OC / 4; ++q) {
-            float4 t = v4[q];
-            acc[4 * q + 0] = fmaf(c, t.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(c, t.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(c, t.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(c, t.w, acc[4 * q + 3]);
-          }
-        }
-        float *mp = msg + (size_t)e * out + c0;
-#pragma unroll
-        for (int o = 0; o < OC; ++o)
-          if (c0 + o < out) mp[o] = v * acc[o];
+        for (int q = 0; q < 8; ++q)
+          if (b0 + q < B) dst[(size_t)(b0 + q) * TJ * OP] = tmp[q];
       }
     }
+    __syncthreads();
+    ident_msg_tile<OC, 4>(Vs, (size_t)TJ * OP, OP, comp_smem ? comp_s : nullptr, CS, comp, B, out, j0, e_lo, e_hi, e2_src,
+                          e2_rel, e2_val, msg);
   }
 }
 
@@ -100,7 +190,8 @@ k_ident_msg_fwd(const float *__restrict__ V, const float *__restrict__ comp, con
 // Feature term (graph.py:93-95 re-associated: no (R,N,out) projection), relation-major.
 //   msg[e3, :] = val_e * X[j_e, :] . W[r, :, :]          one CTA = one chunk of edges of ONE relation
 // smem: Ws[INP][OC] for the current output chunk (INP = in rounded up to KC, pad rows zero),
-//       Xs[warp][32][KC+1] staging of X rows (coalesced loads, conflict-free column reads).
+//       Xs[warp][2][32][KC+1]: rows of X for 32 edges, KC columns at a time, double buffered with cp.async
+//       (coalesced 128-byte row segments in flight while the previous segment is multiplied).
 constexpr int KC = 32;
 template <int OC>
 __global__ void __launch_bounds__(kThreads)
@@ -109,14 +200,16 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
                const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {
   extern __shared__ __align__(16) float smem[];
   float *Ws = smem;                         // [INP][OC]
-  float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][32][KC+1]
+  float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][2][32][KC+1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = kThreads / 32;
-  float *Xs = Xs_all + (size_t)warp * 32 * (KC + 1);
+  constexpr int XB = 32 * (KC + 1);
+  float *Xs = Xs_all + (size_t)warp * 2 * XB;
   const int c = blockIdx.x;
   const int r = chunk_rel[c];
   const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
   const float *Wr = W + (size_t)r * in * out;
+  const int nkc = INP / KC;
   for (int c0 = 0; c0 < out; c0 += OC) {
     __syncthreads();
     for (int x = tid; x < INP * OC; x += kThreads) {
@@ -128,21 +221,32 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
       const int e = eb + lane;
       const bool live = e < e_hi;
       const int j = live ? e3_src[e] : -1;
+      auto prefetch = [&](int kc, int buf) {
+        float *dst = Xs + buf * XB + lane;
+        const int k = kc * KC + lane;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int ji = __shfl_sync(0xffffffffu, j, i);
+          const bool ok = ji >= 0 && k < in;
+          cp_async4(dst + i * (KC + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+        }
+        cp_async_commit();
+      };
       float acc[OC];
 #pragma unroll
       for (int o = 0; o < OC; ++o) acc[o] = 0.f;
-      for (int k0 = 0; k0 < in; k0 += KC) {
-        __syncwarp();
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          int ji = __shfl_sync(0xffffffffu, j, i);
-          float x = 0.f;
-          if (ji >= 0 && k0 + lane < in) x = X[(size_t)ji * in + k0 + lane];
-          Xs[i * (KC + 1) + lane] = x;
+      __syncwarp();
+      prefetch(0, 0);
+      for (int kc = 0; kc < nkc; ++kc) {
+        if (kc + 1 < nkc) {
+          prefetch(kc + 1, (kc + 1) & 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
         }
         __syncwarp();
-        const float *xrow = Xs + lane * (KC + 1);
-        const float *wk = Ws + (size_t)k0 * OC;
+        const float *xrow = Xs + (kc & 1) * XB + lane * (KC + 1);
+        const float *wk = Ws + (size_t)kc * KC * OC;
 #pragma unroll 4
         for (int kk = 0; kk < KC; ++kk) {
           const float x = xrow[kk];
@@ -156,6 +260,7 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
             acc[4 * q + 3] = fmaf(x, t.w, acc[4 * q + 3]);
           }
         }
+        __syncwarp();  // all lanes done with buffer (kc & 1) before it is refilled two chunks later
       }
       if (live) {
         const float v = e3_val[e];
@@ -186,22 +291,36 @@ struct AggArgs {
   int ND, odim, relu, thresh;
 };
 
-__device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int beg, int end, int step) {
+// sum of msg[perm[e]][o] over e = lo+beg, lo+beg+step, ... < hi; four gathers in flight, fixed order
+__device__ __forceinline__ float gather_sum(const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi,
+                                            int beg, int step, int od, int o, float acc) {
+  int e = lo + beg;
+  for (; e + 3 * step < hi; e += 4 * step) {
+    const int p0 = perm[e], p1 = perm[e + step], p2 = perm[e + 2 * step], p3 = perm[e + 3 * step];
+    const float v0 = msg[(size_t)p0 * od + o], v1 = msg[(size_t)p1 * od + o];
+    const float v2 = msg[(size_t)p2 * od + o], v3 = msg[(size_t)p3 * od + o];
+    acc += v0; acc += v1; acc += v2; acc += v3;
+  }
+  for (; e < hi; e += step) acc += msg[(size_t)perm[e] * od + o];
+  return acc;
+}
+
+__device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int beg, int step) {
   float acc = 0.f;
   const int od = a.odim;
-  int lo = a.rowptr ? a.rowptr[i] : 0, hi = a.rowptr ? a.rowptr[i + 1] : 0;
-  if (a.msgI) {
-    for (int e = lo + beg; e < hi; e += step) acc += a.msgI[(size_t)a.pI[e] * od + o];
-  }
+  const int lo = a.rowptr ? a.rowptr[i] : 0, hi = a.rowptr ? a.rowptr[i + 1] : 0;
+  if (a.msgI) acc = gather_sum(a.msgI, a.pI, lo, hi, beg, step, od, o, acc);
   if (a.Wd) {
-    for (int e = lo + beg; e < hi; e += step)
-      acc = fmaf(a.d_val[e], a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o], acc);
+    int e = lo + beg;
+    for (; e + step < hi; e += 2 * step) {
+      const float w0 = a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o];
+      const float w1 = a.Wd[((size_t)a.d_rel[e + step] * a.NSd + a.d_src[e + step]) * od + o];
+      acc = fmaf(a.d_val[e], w0, acc);
+      acc = fmaf(a.d_val[e + step], w1, acc);
+    }
+    for (; e < hi; e += step) acc = fmaf(a.d_val[e], a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o], acc);
   }
-  if (a.msgF) {
-    int lf = a.rowptrF[i], hf = a.rowptrF[i + 1];
-    for (int e = lf + beg; e < hf; e += step) acc += a.msgF[(size_t)a.pF[e] * od + o];
-  }
-  (void)end;
+  if (a.msgF) acc = gather_sum(a.msgF, a.pF, a.rowptrF[i], a.rowptrF[i + 1], beg, step, od, o, acc);
   return acc;
 }
 
@@ -229,14 +348,14 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
     int i = gw;
     if (i >= a.ND) return;
     if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
-    for (int o = lane; o < od; o += 32) agg_store(a, i, o, agg_edges(a, i, o, 0, 0, 1));
+    for (int o = lane; o < od; o += 32) agg_store(a, i, o, agg_edges(a, i, o, 0, 1));
   } else {
     const int rpw = 32 / od;
     const int slot = lane / od, o = lane - slot * od;
     int i = gw * rpw + slot;
     if (slot >= rpw || i >= a.ND) return;
     if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
-    agg_store(a, i, o, agg_edges(a, i, o, 0, 0, 1));
+    agg_store(a, i, o, agg_edges(a, i, o, 0, 1));
   }
 }
 
@@ -251,7 +370,7 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd_long(AggArgs a, const int3
   for (int o0 = 0; o0 < od; o0 += oc) {
     const int o = o0 + ol;
     float acc = 0.f;
-    if (slot < nslots && o < od) acc = agg_edges(a, i, o, slot, 0, nslots);
+    if (slot < nslots && o < od) acc = agg_edges(a, i, o, slot, nslots);
     if (slot < nslots) red[slot * oc + ol] = acc;
     __syncthreads();
     for (int s = 1; s < nslots; s <<= 1) {
@@ -298,16 +417,67 @@ int ident_tile(int B, int out, int OP) {
   return tj;
 }
 
+// tile of the TMA-engine variants: largest TJ with TJ*out <= 256 floats and 16-byte runs; 0 = not applicable
+int ident_tile_bulk(int64_t NS, int out) {
+  if ((NS * out) % 4 != 0) return 0;
+  int tj = 256 / out;
+  if (tj < 1) tj = 1;
+  while (tj > 0 && (tj * out) % 4 != 0) --tj;
+  if (tj <= 0 && (out % 4) == 0) tj = 1;
+  if (tj <= 0 || tj > NS) return 0;
+  return tj;
+}
+
 static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const float *comp, float *msg, int B, int out,
                                 cudaStream_t st) {
   const int OC = pick_oc(out);
-  const int OP = (int)cdiv(out, OC) * OC;
-  const int TJ = ident_tile(B, out, OP);
   const int CS = B | 1;
   const int comp_smem = ((size_t)g->R * CS * 4 <= 64 * 1024) ? 1 : 0;
-  size_t smem = (comp_smem ? (((size_t)g->R * CS + 3) & ~(size_t)3) : 0) * 4 + (size_t)B * TJ * OP * 4;
-  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "ident_msg_fwd: B*out too large for shared memory (%zu B)", smem);
+  const size_t comp_bytes = (comp_smem ? (((size_t)g->R * CS + 3) & ~(size_t)3) : 0) * 4;
   unsigned grid = 0;
+  const int TJb = ident_tile_bulk(g->NS, out);
+  if (TJb > 0) {
+    const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
+    const int stage_floats = ((B * TJb * out + 3) & ~3) + 16;
+    int S = 4;
+    size_t smem = 0;
+    for (; S >= 2; --S) {
+      smem = 16 * ((S * 8 + 15) / 16) + comp_bytes + (size_t)S * stage_floats * 4;
+      if (smem <= 200 * 1024) break;
+    }
+    if (S >= 2) {
+      const int ntiles = (int)cdiv(g->NS, TJb);
+      MRGCN_PROF("ident_msg_fwd");
+#define LAUNCH(OCV, VWV)                                                                                           \
+  do {                                                                                                             \
+    if (int rc = set_smem(k_ident_msg_fwd_bulk<OCV, VWV>, smem)) return rc;                                        \
+    grid = persistent_grid(k_ident_msg_fwd_bulk<OCV, VWV>, kThreads, smem, ntiles);                                \
+    k_ident_msg_fwd_bulk<OCV, VWV><<<grid, kThreads, smem, st>>>(V, comp, g->colptr, g->e2_src, g->e2_rel, g->e2_val, \
+                                                                 msg, g->NS, g->R, B, out, TJb, CS, comp_smem, S,  \
+                                                                 stage_floats, ntiles);                            \
+  } while (0)
+#define LAUNCH_VW(OCV)                                   \
+  do {                                                   \
+    if (VW == 4) LAUNCH(OCV, 4);                         \
+    else if (VW == 2) LAUNCH(OCV, 2);                    \
+    else LAUNCH(OCV, 1);                                 \
+  } while (0)
+      switch (OC) {
+        case 4: LAUNCH_VW(4); break;
+        case 8: LAUNCH_VW(8); break;
+        case 12: LAUNCH_VW(12); break;
+        default: LAUNCH_VW(16); break;
+      }
+#undef LAUNCH_VW
+#undef LAUNCH
+      MRGCN_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  const int OP = (int)cdiv(out, OC) * OC;
+  const int TJ = ident_tile(B, out, OP);
+  size_t smem = comp_bytes + (size_t)B * TJ * OP * 4;
+  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "ident_msg_fwd: B*out too large for shared memory (%zu B)", smem);
 #define LAUNCH(OCV)                                                                                               \
   do {                                                                                                            \
     if (int rc = set_smem(k_ident_msg_fwd<OCV>, smem)) return rc;                                                 \
@@ -332,7 +502,7 @@ static int launch_feat_msg_fwd(const mrgcn_graph *g, const float *X, const float
   if (g->n_chunks == 0) return 0;
   const int OC = pick_oc(out);
   const int INP = (int)cdiv(in, KC) * KC;
-  size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 32 * (KC + 1)) * 4;
+  size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 2 * 32 * (KC + 1)) * 4;
   MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "feat_msg_fwd: in too large for shared memory (%zu B)", smem);
 #define LAUNCH(OCV)                                                                                            \
   do {                                                                                                         \

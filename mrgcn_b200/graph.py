@@ -18,7 +18,7 @@ import torch
 
 from . import _native as nv
 
-LONG_THRESH = 512      # rows / sources with more edges than this get a CTA of their own
+LONG_THRESH = 128      # rows / sources with more edges than this get a CTA of their own
 _I32 = torch.int32
 
 

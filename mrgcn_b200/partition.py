@@ -131,8 +131,12 @@ class PartitionedRGCN(nn.Module):
     rank's slice [:, lo:hi, :] of the reference tensor (rows b*n_p + (j - lo))."""
 
     def __init__(self, modules, num_relations, num_nodes, num_bases, featureless, bias, link_prediction,
-                 bounds, rank, group=None):
+                 bounds, rank, group=None, layer_fn=None, graph_fn=None):
+        """layer_fn / graph_fn: test seams (tests/test_partition_gloo.py drives the partition logic and the
+        collectives on CPU with the oracle's layer arithmetic); the product default is the CUDA layer."""
         super().__init__()
+        self._layer_fn = layer_fn or _LayerFn.apply
+        self._graph_fn = graph_fn or RelGraph.from_coo_arrays
         self.lay = _Layout(bounds, rank, group)
         self.num_nodes, self.num_relations, self.num_bases = num_nodes, num_relations, num_bases
         self.featureless = featureless
@@ -156,8 +160,8 @@ class PartitionedRGCN(nn.Module):
         lay = self.lay
         feat, ident = split_coo(row, col, val, self.num_nodes, self.num_relations, lay.lo, lay.hi)
         n_p = lay.hi - lay.lo
-        self.gF = RelGraph.from_coo_arrays(*feat, n_p, self.num_relations * self.num_nodes, self.num_relations)
-        self.gI = RelGraph.from_coo_arrays(*ident, self.num_nodes, self.num_relations * n_p, self.num_relations)
+        self.gF = self._graph_fn(*feat, n_p, self.num_relations * self.num_nodes, self.num_relations)
+        self.gI = self._graph_fn(*ident, self.num_nodes, self.num_relations * n_p, self.num_relations)
 
     def load_full_state(self, full_state):
         """Take this rank's share of an unpartitioned RGCN state_dict (checkpoint interchange)."""
@@ -177,18 +181,18 @@ class PartitionedRGCN(nn.Module):
         for k, (layer, act) in enumerate(zip(self.layers.values(), self.activations.values())):
             relu = isinstance(act, nn.ReLU)
             if k == 0:
-                part = _LayerFn.apply(None, layer.weight_I, layer.weight_I_comp, None, None, None, None, self.gI, None,
+                part = self._layer_fn(None, layer.weight_I, layer.weight_I_comp, None, None, None, None, self.gI, None,
                                       self.num_bases, False)                       # (N, out) partial, my sources only
                 own = ScatterSumRows.apply(part, lay)                              # (n_p, out)
                 if layer.featureless:
                     H = own if layer.b is None else own + layer.b
                     H = torch.relu(H) if relu else H
                 else:
-                    H = _LayerFn.apply(X, None, None, layer.weight_F, layer.weight_F_comp, layer.b, None, None, self.gF,
+                    H = self._layer_fn(X, None, None, layer.weight_F, layer.weight_F_comp, layer.b, None, None, self.gF,
                                        self.num_bases, relu, own)
             else:
                 Hall = GatherRows.apply(H, lay)                                    # (N, d)
-                H = _LayerFn.apply(Hall, None, None, layer.weight_F, layer.weight_F_comp, layer.b, None, None, self.gF,
+                H = self._layer_fn(Hall, None, None, layer.weight_F, layer.weight_F_comp, layer.b, None, None, self.gF,
                                    self.num_bases, relu)
             if act is not None and not relu:
                 H = act(H)
