@@ -65,6 +65,7 @@ typedef struct mrgcn_graph {
   int32_t *e2_dst;   /* [E] */
   int32_t *e2_rel;   /* [E] */
   float   *e2_val;   /* [E] */
+  int32_t *e2_to_e3; /* [E] position of the same edge in E3 */
   /* E3 */
   int32_t *relptr;   /* [R+1] */
   int32_t *e3_src;   /* [E] */
@@ -133,12 +134,14 @@ int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);
  *   g_X [NS_F,in]
  * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term);
  *   part [n_chunks * max(B, in*out)] ; g_wmix [R*in*out] (B>0 and feature term);
- *   colsum_ws [ceil(ND/1024) * out]. */
+ *   colsum_ws [ceil(ND/1024) * out]; wt_ws, msgx_ws when g_X is wanted. */
 typedef struct mrgcn_layer_bwd_args {
   mrgcn_layer_args f;     /* forward arguments (out = forward result, wmix as filled by forward) */
   const float *gout;
   float *g_weight_I, *g_comp_I, *g_weight_F, *g_comp_F, *g_bias, *g_X;
   float *gact, *cbuf, *part, *g_wmix, *colsum_ws;
+  float *wt_ws;   /* [R*in*out]  (g_X wanted) transposed weights */
+  float *msgx_ws; /* [E_F*in]    (g_X wanted) per-edge input-gradient messages */
 } mrgcn_layer_bwd_args;
 int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_t stream);
 

@@ -24,7 +24,7 @@ class Graph(C.Structure):
         ("rowptr", C.c_void_p), ("e1_src", C.c_void_p), ("e1_rel", C.c_void_p), ("e1_val", C.c_void_p),
         ("e1_to_e2", C.c_void_p), ("e1_to_e3", C.c_void_p),
         ("colptr", C.c_void_p), ("e2_src", C.c_void_p), ("e2_dst", C.c_void_p), ("e2_rel", C.c_void_p),
-        ("e2_val", C.c_void_p),
+        ("e2_val", C.c_void_p), ("e2_to_e3", C.c_void_p),
         ("relptr", C.c_void_p), ("e3_src", C.c_void_p), ("e3_dst", C.c_void_p), ("e3_val", C.c_void_p),
         ("e3_to_e2", C.c_void_p),
         ("long_rows", C.c_void_p), ("n_long_rows", C.c_int32), ("long_row_thresh", C.c_int32),
@@ -53,7 +53,7 @@ class LayerBwdArgs(C.Structure):
         ("g_weight_I", C.c_void_p), ("g_comp_I", C.c_void_p), ("g_weight_F", C.c_void_p),
         ("g_comp_F", C.c_void_p), ("g_bias", C.c_void_p), ("g_X", C.c_void_p),
         ("gact", C.c_void_p), ("cbuf", C.c_void_p), ("part", C.c_void_p), ("g_wmix", C.c_void_p),
-        ("colsum_ws", C.c_void_p),
+        ("colsum_ws", C.c_void_p), ("wt_ws", C.c_void_p), ("msgx_ws", C.c_void_p),
     ]
 
 

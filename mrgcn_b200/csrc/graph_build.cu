@@ -131,7 +131,8 @@ __global__ void k_fill_e3(const int32_t *__restrict__ e3_to_e2_in, const int32_t
                           const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
                           int32_t *__restrict__ e3_src, int32_t *__restrict__ e3_dst,
                           int32_t *__restrict__ e3_rel, float *__restrict__ e3_val,
-                          int32_t *__restrict__ e3_to_e2, int32_t *__restrict__ e1_to_e3, int64_t E) {
+                          int32_t *__restrict__ e3_to_e2, int32_t *__restrict__ e1_to_e3, int32_t *__restrict__ e2_to_e3,
+                          int64_t E) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= E) return;
   int32_t q = e3_to_e2_in[t];
@@ -140,6 +141,7 @@ __global__ void k_fill_e3(const int32_t *__restrict__ e3_to_e2_in, const int32_t
   e3_rel[t] = e2_rel[q];
   e3_val[t] = e2_val[q];
   e3_to_e2[t] = q;
+  e2_to_e3[q] = (int32_t)t;
   e1_to_e3[e2_to_e1[q]] = (int32_t)t;
 }
 
@@ -299,7 +301,7 @@ extern "C" int mrgcn_graph_build(const int64_t *coo_row, const int64_t *coo_col,
     int b3 = bits_for((uint64_t)R);
     if (int rc = sort_pairs(kA.as<uint32_t>(), kB.as<uint32_t>(), vA.as<int32_t>(), vB.as<int32_t>(), E, b3, st)) return rc;
     k_fill_e3<<<gridE, T, 0, st>>>(vB.as<int32_t>(), e2to1.as<int32_t>(), g->e2_src, g->e2_dst, g->e2_rel, g->e2_val,
-                                   g->e3_src, g->e3_dst, e3rel.as<int32_t>(), g->e3_val, g->e3_to_e2, g->e1_to_e3, E);
+                                   g->e3_src, g->e3_dst, e3rel.as<int32_t>(), g->e3_val, g->e3_to_e2, g->e1_to_e3, g->e2_to_e3, E);
     MRGCN_LAUNCH_CHECK();
   }
   k_ptr<<<(unsigned)cdiv((int64_t)ND + 1, T), T, 0, st>>>(e1dst.as<int32_t>(), E, ND, g->rowptr);

@@ -12,13 +12,10 @@
 // Every reduction is a segmented sum in a fixed order: bit-reproducible, no float atomics.
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "ident_pipe.cuh"
+#include "rgcn_internal.cuh"
 
 namespace mrgcn {
-int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st);
-int pick_oc(int out);
-int ident_tile(int B, int out, int OP);
-int ident_tile_bulk(int64_t NS, int out);
-
 namespace {
 
 constexpr int kThreads = 256;
@@ -69,24 +66,31 @@ k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const 
   }
 }
 
-// out[x] = sum_c part[c*stride + x] for c in [lo, hi) -- sequential, fixed order.
-// seg_ptr == NULL: one segment [0, nseg_total).
-__global__ void k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr, int nall, int width,
-                             float *__restrict__ outp) {
+// out[s, x] = sum_c part[c*width + x] for c in [seg_ptr[s], seg_ptr[s+1]) -- fixed order: 8 chunk slots stride the
+// segment (each slot sequential), then a fixed tree over the slots.  seg_ptr == NULL: one segment [0, nall).
+__global__ void __launch_bounds__(256)
+k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr, int nall, int width,
+             float *__restrict__ outp) {
+  __shared__ float red[8][32];
   const int s = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= width) return;
+  const int xl = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + xl;
   const int lo = seg_ptr ? seg_ptr[s] : 0, hi = seg_ptr ? seg_ptr[s + 1] : nall;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int c = lo;
-  for (; c + 4 <= hi; c += 4) {  // 4 interleaved chains: fixed association, more loads in flight
-    a0 += part[(size_t)c * width + x];
-    a1 += part[(size_t)(c + 1) * width + x];
-    a2 += part[(size_t)(c + 2) * width + x];
-    a3 += part[(size_t)(c + 3) * width + x];
+  float a0 = 0.f, a1 = 0.f;
+  if (x < width) {
+    int c = lo + slot;
+    for (; c + 8 < hi; c += 16) {
+      a0 += part[(size_t)c * width + x];
+      a1 += part[(size_t)(c + 8) * width + x];
+    }
+    if (c < hi) a0 += part[(size_t)c * width + x];
   }
-  for (; c < hi; ++c) a0 += part[(size_t)c * width + x];
-  outp[(size_t)s * width + x] = (a0 + a1) + (a2 + a3);
+  red[slot][xl] = a0 + a1;
+  __syncthreads();
+  if (slot == 0 && x < width) {
+    float t = ((red[0][xl] + red[1][xl]) + (red[2][xl] + red[3][xl])) + ((red[4][xl] + red[5][xl]) + (red[6][xl] + red[7][xl]));
+    outp[(size_t)s * width + x] = t;
+  }
 }
 
 // ---- identity term, B == 0: one thread group per E2 edge that starts a (src, rel) run ------------
@@ -118,103 +122,77 @@ k_ident_bwd_direct(const int32_t *__restrict__ e2_src, const int32_t *__restrict
 // ---- identity term, B > 0, comp gradient contributions: cbuf[e2, b] = <V[b, j_e, :], t_e> ----------
 // Same tiling / TMA-engine staging as k_ident_msg_fwd_bulk (rgcn_fwd.cu); one edge per lane, the lane's B
 // results are 160 contiguous bytes of cbuf (16-byte stores when B % 4 == 0).
+// per-edge body shared by both variants: B dot products <V[b, j, :], t_e> -> cbuf[e, 0:B]
 template <int OC, int VW>
-__device__ __forceinline__ void ident_bwd_c_tile(const float *__restrict__ Vs, size_t bstride, int RS, int B, int out, int j0,
-                                                 int e_lo, int e_hi, const int32_t *__restrict__ e2_src,
-                                                 const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val,
-                                                 const float *__restrict__ gact, float *__restrict__ cbuf) {
-  for (int e = e_lo + threadIdx.x; e < e_hi; e += kThreads) {
-    const int jl = e2_src[e] - j0;
-    const float v = e2_val[e];
-    const float *gp = gact + (size_t)e2_dst[e] * out;
-    float *cp = cbuf + (size_t)e * B;
-    for (int c0 = 0; c0 < out; c0 += OC) {
-      float t[OC];
+__device__ __forceinline__ void ident_bwd_c_edge(const float *__restrict__ vrow, size_t bstride, int B, int out, float v,
+                                                 const float *__restrict__ gp, float *__restrict__ cp) {
+  for (int c0 = 0; c0 < out; c0 += OC) {
+    float t[OC];
 #pragma unroll
-      for (int o = 0; o < OC; ++o) t[o] = (c0 + o < out) ? v * gp[c0 + o] : 0.f;
-      const float *vp = Vs + (size_t)jl * RS + c0;
-      auto dot = [&](int b) {
-        const float *row = vp + (size_t)b * bstride;
-        float acc = 0.f;
-        if constexpr (VW == 4) {
+    for (int o = 0; o < OC; ++o) t[o] = (c0 + o < out) ? v * gp[c0 + o] : 0.f;
+    const float *vp = vrow + c0;
+    auto dot = [&](int b) {
+      const float *row = vp + (size_t)b * bstride;
+      float acc = 0.f;
+      if constexpr (VW == 4) {
 #pragma unroll
-          for (int q = 0; q < OC / 4; ++q) {
-            float4 w = reinterpret_cast<const float4 *>(row)[q];
-            acc = fmaf(w.x, t[4 * q + 0], acc); acc = fmaf(w.y, t[4 * q + 1], acc);
-            acc = fmaf(w.z, t[4 * q + 2], acc); acc = fmaf(w.w, t[4 * q + 3], acc);
-          }
-        } else if constexpr (VW == 2) {
-#pragma unroll
-          for (int q = 0; q < OC / 2; ++q) {
-            float2 w = reinterpret_cast<const float2 *>(row)[q];
-            acc = fmaf(w.x, t[2 * q + 0], acc); acc = fmaf(w.y, t[2 * q + 1], acc);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < OC; ++q)
-            if (c0 + q < out) acc = fmaf(row[q], t[q], acc);   // VW==1 rows may end at the buffer edge
+        for (int q = 0; q < OC / 4; ++q) {
+          float4 w = reinterpret_cast<const float4 *>(row)[q];
+          acc = fmaf(w.x, t[4 * q + 0], acc); acc = fmaf(w.y, t[4 * q + 1], acc);
+          acc = fmaf(w.z, t[4 * q + 2], acc); acc = fmaf(w.w, t[4 * q + 3], acc);
         }
-        return acc;
-      };
-      if ((B & 3) == 0) {
-#pragma unroll 2
-        for (int b = 0; b < B; b += 4) {
-          float4 c = make_float4(dot(b), dot(b + 1), dot(b + 2), dot(b + 3));
-          float4 *dst = reinterpret_cast<float4 *>(cp + b);
-          if (c0 > 0) { float4 p = *dst; c.x += p.x; c.y += p.y; c.z += p.z; c.w += p.w; }
-          *dst = c;
+      } else if constexpr (VW == 2) {
+#pragma unroll
+        for (int q = 0; q < OC / 2; ++q) {
+          float2 w = reinterpret_cast<const float2 *>(row)[q];
+          acc = fmaf(w.x, t[2 * q + 0], acc); acc = fmaf(w.y, t[2 * q + 1], acc);
         }
       } else {
-        for (int b = 0; b < B; ++b) {
-          float c = dot(b);
-          if (c0 > 0) c += cp[b];
-          cp[b] = c;
-        }
+#pragma unroll
+        for (int q = 0; q < OC; ++q)
+          if (c0 + q < out) acc = fmaf(row[q], t[q], acc);
+      }
+      return acc;
+    };
+    if ((B & 3) == 0) {
+#pragma unroll 2
+      for (int b = 0; b < B; b += 4) {
+        float4 c = make_float4(dot(b), dot(b + 1), dot(b + 2), dot(b + 3));
+        float4 *dst = reinterpret_cast<float4 *>(cp + b);
+        if (c0 > 0) { float4 q = *dst; c.x += q.x; c.y += q.y; c.z += q.z; c.w += q.w; }
+        *dst = c;
+      }
+    } else {
+      for (int b = 0; b < B; ++b) {
+        float c = dot(b);
+        if (c0 > 0) c += cp[b];
+        cp[b] = c;
       }
     }
   }
 }
 
 template <int OC, int VW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPipeThreads)
 k_ident_bwd_c_bulk(const float *__restrict__ V, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_src,
                    const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val, const float *__restrict__ gact,
-                   float *__restrict__ cbuf, int NS, int B, int out, int TJ, int S, int stage_floats, int ntiles) {
+                   float *__restrict__ cbuf, IdentPipe p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-  float *stages = reinterpret_cast<float *>(smem_raw + 16 * ((S * 8 + 15) / 16));
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *empty = full + p.S;
+  unsigned char *stages = smem_raw + 16 * ((2 * p.S * 8 + 15) / 16);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kPipeConsumerWarps); }
     mbar_fence_init();
   }
   __syncthreads();
-  const uint32_t run_bytes = (uint32_t)TJ * out * 4;
-  auto issue = [&](int k) {
-    const int t = blockIdx.x + k * gridDim.x;
-    if (t >= ntiles) return;
-    const int s = k % S;
-    int j0 = t * TJ;
-    if (j0 + TJ > NS) j0 = NS - TJ;
-    float *dst = stages + (size_t)s * stage_floats;
-    fence_proxy_async();
-    mbar_expect_tx(&bars[s], run_bytes * B);
-    for (int b = 0; b < B; ++b) bulk_g2s(dst + (size_t)b * TJ * out, V + ((size_t)b * NS + j0) * out, run_bytes, &bars[s]);
-  };
-  if (tid == 0)
-    for (int k = 0; k < S - 1; ++k) issue(k);
-  for (int k = 0;; ++k) {
-    const int t = blockIdx.x + k * gridDim.x;
-    if (t >= ntiles) break;
-    if (tid == 0) issue(k + S - 1);
-    int j0 = t * TJ;
-    if (j0 + TJ > NS) j0 = NS - TJ;
-    const int e_lo = colptr[j0], e_hi = colptr[j0 + TJ];
-    mbar_wait(&bars[k % S], (k / S) & 1);
-    ident_bwd_c_tile<OC, VW>(stages + (size_t)(k % S) * stage_floats, (size_t)TJ * out, out, B, out, j0, e_lo, e_hi, e2_src,
-                             e2_dst, e2_val, gact, cbuf);
-    __syncthreads();
-  }
+  const int B = p.B, out = p.out;
+  const size_t bstride = (size_t)p.TJ * out;
+  ident_pipeline(p, V, colptr, e2_src, e2_dst, e2_val, stages, full, empty,
+                 [&](const float *vs, int j0, int e, int src, int dst, float v) {
+                   ident_bwd_c_edge<OC, VW>(vs + (size_t)(src - j0) * out, bstride, B, out, v, gact + (size_t)dst * out,
+                                            cbuf + (size_t)e * B);
+                 });
 }
 
 // generic variant (any alignment): cooperative loads into a padded tile Vs[B][TJ][OP], pad columns zeroed
@@ -252,7 +230,9 @@ k_ident_bwd_c(const float *__restrict__ V, const int32_t *__restrict__ colptr, c
         Vs[((size_t)b * TJ + jl) * OP + o] = 0.f;
       }
     __syncthreads();
-    ident_bwd_c_tile<OC, 4>(Vs, (size_t)TJ * OP, OP, B, out, j0, e_lo, e_hi, e2_src, e2_dst, e2_val, gact, cbuf);
+    for (int e = e_lo + tid; e < e_hi; e += kThreads)
+      ident_bwd_c_edge<OC, 4>(Vs + (size_t)(e2_src[e] - j0) * OP, (size_t)TJ * OP, B, out, e2_val[e],
+                              gact + (size_t)e2_dst[e] * out, cbuf + (size_t)e * B);
   }
 }
 
@@ -358,50 +338,54 @@ k_ident_bwd_w_generic(const float *__restrict__ comp, const int32_t *__restrict_
   }
 }
 
-// hubs: one CTA per long source.  Rounds of EC edges are staged like above; thread p owns the (basis, o) pairs
-// p, p + 256, ... and walks the staged edges sequentially (fixed order).
-__global__ void __launch_bounds__(kThreads)
+// hubs: one CTA (1024 threads) per long source.  Rounds of EL edges are staged like above; comp is resident in
+// shared memory; thread p owns the (basis, o) pairs p, p + 1024, ... and walks the staged edges in order.
+constexpr int kHubThreads = 1024;
+__global__ void __launch_bounds__(kHubThreads)
 k_ident_bwd_w_long(const float *__restrict__ comp, const int32_t *__restrict__ long_cols,
                    const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
                    const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
-                   const float *__restrict__ gact, float *__restrict__ gW, int64_t NS, int B, int out, int EL) {
+                   const float *__restrict__ gact, float *__restrict__ gW, int64_t NS, int R, int B, int out, int EL,
+                   int comp_smem) {
   extern __shared__ __align__(16) float smem[];
   float *Ts = smem;                                          // [EL][out]
-  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EL * out);  // [EL]
+  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EL * out);  // [EL]  (pre-multiplied by B)
+  float *comp_s = reinterpret_cast<float *>(Rs + EL);        // [R][B]
   const int j = long_cols[blockIdx.x];
   const int e_lo = colptr[j], e_hi = colptr[j + 1];
   const int tid = threadIdx.x;
+  if (comp_smem)
+    for (int x = tid; x < R * B; x += kHubThreads) comp_s[x] = __ldg(comp + x);
+  const float *cbase = comp_smem ? comp_s : comp;
   const int npairs = B * out;
-  for (int p0 = 0; p0 < npairs; p0 += 4 * kThreads) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int pb[4], po[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int p = p0 + q * kThreads + tid;
-      pb[q] = p < npairs ? p / out : -1;
-      po[q] = p < npairs ? p - pb[q] * out : 0;
-    }
+  for (int p0 = 0; p0 < npairs; p0 += 2 * kHubThreads) {
+    float acc0 = 0.f, acc1 = 0.f;
+    const int pa = p0 + tid, pb = p0 + kHubThreads + tid;
+    const bool va = pa < npairs, vb = pb < npairs;
+    const int ba = va ? pa / out : 0, oa = va ? pa - ba * out : 0;
+    const int bb = vb ? pb / out : 0, ob = vb ? pb - bb * out : 0;
     for (int c_lo = e_lo; c_lo < e_hi; c_lo += EL) {
       const int n = min(EL, e_hi - c_lo);
       __syncthreads();
-      for (int el = tid; el < n; el += kThreads) {
+      for (int el = tid; el < n; el += kHubThreads) {
         const int e = c_lo + el;
         const float v = e2_val[e];
         const float *gp = gact + (size_t)e2_dst[e] * out;
-        Rs[el] = e2_rel[e];
+        Rs[el] = e2_rel[e] * B;
         for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
       }
       __syncthreads();
-      for (int el = 0; el < n; ++el) {
-        const float *cr = comp + (size_t)Rs[el] * B;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (pb[q] >= 0) acc[q] = fmaf(__ldg(cr + pb[q]), Ts[el * out + po[q]], acc[q]);
+      if (va) {
+#pragma unroll 4
+        for (int el = 0; el < n; ++el) {
+          const float *cr = cbase + Rs[el];
+          acc0 = fmaf(cr[ba], Ts[el * out + oa], acc0);
+          if (vb) acc1 = fmaf(cr[bb], Ts[el * out + ob], acc1);
+        }
       }
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (pb[q] >= 0) gW[((size_t)pb[q] * NS + j) * out + po[q]] = acc[q];
+    if (va) gW[((size_t)ba * NS + j) * out + oa] = acc0;
+    if (vb) gW[((size_t)bb * NS + j) * out + ob] = acc1;
   }
 }
 
@@ -510,94 +494,16 @@ k_basis_mix_bwd_c(const float *__restrict__ V, const float *__restrict__ gW, flo
   if (threadIdx.x == 0) gcomp[(size_t)r * B + b] = red[0];
 }
 
-// ---- input gradient: g_X[j,k] = sum_{e: src=j} val_e * sum_o gact[dst_e,o] * W[r_e,k,o] -------------
-// Tiles of TJ sources (TJ*in <= 256): t_e staged per round in shared memory (independent gathers), one thread per
-// (j,k) walks the source's staged edges; W rows come through L1/L2 (R*in*out floats, hot relations stay in L1).
-__global__ void __launch_bounds__(kThreads)
-k_feat_bwd_x(const float *__restrict__ W, const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
-             const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
-             float *__restrict__ gX, int NS, int in, int out, int TJ, int thresh, int EC) {
-  extern __shared__ __align__(16) float smem[];
-  float *Ts = smem;                                          // [EC][out]
-  int *Rs = reinterpret_cast<int *>(Ts + (size_t)EC * out);  // [EC]
-  const int tid = threadIdx.x;
-  for (int j0 = blockIdx.x * TJ; j0 < NS; j0 += gridDim.x * TJ) {
-    const int tjw = min(TJ, NS - j0);
-    const int t_lo = colptr[j0], t_hi = colptr[j0 + tjw];
-    for (int k0 = 0; k0 < in; k0 += kThreads) {   // in > 256 only: TJ == 1, columns in rounds
-      const int cols = TJ == 1 ? min(kThreads, in - k0) : tjw * in;
-      const bool mine = tid < cols;
-      const int jl = (mine && TJ > 1) ? tid / in : 0;
-      const int k = TJ > 1 ? tid - jl * in : k0 + tid;
-      int s_lo = 0, s_hi = 0;
-      bool hub = false;
-      if (mine) {
-        s_lo = colptr[j0 + jl];
-        s_hi = colptr[j0 + jl + 1];
-        hub = thresh > 0 && s_hi - s_lo > thresh;
-        if (hub) s_hi = s_lo;
-      }
-      float acc = 0.f;
-      for (int c_lo = t_lo; c_lo < t_hi; c_lo += EC) {
-        const int c_hi = min(t_hi, c_lo + EC);
-        __syncthreads();
-        for (int el = tid; el < c_hi - c_lo; el += kThreads) {
-          const int e = c_lo + el;
-          const float v = e2_val[e];
-          const float *gp = gact + (size_t)e2_dst[e] * out;
-          Rs[el] = e2_rel[e];
-          for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
-        }
-        __syncthreads();
-        const int lo = max(s_lo, c_lo), hi = min(s_hi, c_hi);
-        for (int e = lo; e < hi; ++e) {
-          const float *tp = Ts + (e - c_lo) * out;
-          const float *wp = W + ((size_t)Rs[e - c_lo] * in + k) * out;
-          float d0 = 0.f, d1 = 0.f;
-          int q = 0;
-          for (; q + 1 < out; q += 2) {
-            d0 = fmaf(tp[q], __ldg(wp + q), d0);
-            d1 = fmaf(tp[q + 1], __ldg(wp + q + 1), d1);
-          }
-          if (q < out) d0 = fmaf(tp[q], __ldg(wp + q), d0);
-          acc += d0 + d1;
-        }
-      }
-      if (mine && !hub) gX[(size_t)(j0 + jl) * in + k] = acc;
-      if (TJ > 1) break;
-    }
-  }
-}
-__global__ void __launch_bounds__(kThreads)
-k_feat_bwd_x_long(const float *__restrict__ W, const int32_t *__restrict__ long_cols, const int32_t *__restrict__ colptr,
-                  const int32_t *__restrict__ e2_dst, const int32_t *__restrict__ e2_rel,
-                  const float *__restrict__ e2_val, const float *__restrict__ gact, float *__restrict__ gX, int in,
-                  int out) {
-  __shared__ float red[kThreads];
-  const int j = long_cols[blockIdx.x];
-  const int e_lo = colptr[j], e_hi = colptr[j + 1];
-  const int kc = min(in, kThreads), nslots = kThreads / kc;
-  const int slot = threadIdx.x / kc, kl = threadIdx.x - slot * kc;
-  for (int k0 = 0; k0 < in; k0 += kc) {
-    const int k = k0 + kl;
-    float acc = 0.f;
-    if (slot < nslots && k < in)
-      for (int e = e_lo + slot; e < e_hi; e += nslots) {
-        const float *gp = gact + (size_t)e2_dst[e] * out;
-        const float *wp = W + ((size_t)e2_rel[e] * in + k) * out;
-        float d = 0.f;
-        for (int o = 0; o < out; ++o) d = fmaf(gp[o], __ldg(wp + o), d);
-        acc = fmaf(e2_val[e], d, acc);
-      }
-    if (slot < nslots) red[slot * kc + kl] = acc;
-    __syncthreads();
-    for (int s = 1; s < nslots; s <<= 1) {
-      if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * kc + kl] += red[(slot + s) * kc + kl];
-      __syncthreads();
-    }
-    if (slot == 0 && k < in) gX[(size_t)j * in + k] = red[kl];
-    __syncthreads();
-  }
+// ---- input gradient --------------------------------------------------------------------------------
+// g_X[j,:] = sum_{e: src=j} val_e * gact[dst_e,:] . W[r_e]^T  is the forward pass on the transposed graph: the
+// relation-major message kernel gathers gact rows by e3_dst and multiplies with W^T, the segmented sum runs over
+// sources (E2) through e2_to_e3.  Wt[r][o][k] = W[r][k][o]:
+__global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int in, int out) {
+  const int r = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= in * out) return;
+  const int k = x / out, o = x - k * out;
+  Wt[((size_t)r * out + o) * in + k] = W[(size_t)r * in * out + x];
 }
 
 }  // namespace
@@ -627,7 +533,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   if (a->g_bias) {
     if (ND > 0) {
       MRGCN_PROF("bias_reduce");
-  k_seq_reduce<<<dim3((unsigned)cdiv(out, 128), 1), 128, 0, st>>>(a->colsum_ws, nullptr, nblk, out, a->g_bias);
+  k_seq_reduce<<<dim3((unsigned)cdiv(out, 32), 1), 256, 0, st>>>(a->colsum_ws, nullptr, nblk, out, a->g_bias);
       MRGCN_LAUNCH_CHECK();
     } else {
       MRGCN_CUDA(cudaMemsetAsync(a->g_bias, 0, sizeof(float) * out, st));
@@ -684,14 +590,15 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
           MRGCN_LAUNCH_CHECK();
         }
         if (gI->n_long_cols > 0) {
+          const int comp_smem = (size_t)gI->R * B * 4 <= 64 * 1024 ? 1 : 0;
           int EL = 1024;
-          while (EL > 32 && ((size_t)EL * out + EL) * 4 > 96 * 1024) EL >>= 1;
-          size_t smem = ((size_t)EL * out + EL) * 4;
+          while (EL > 32 && ((size_t)EL * out + EL) * 4 > 64 * 1024) EL >>= 1;
+          size_t smem = ((size_t)EL * out + EL + (comp_smem ? (size_t)gI->R * B : 0)) * 4;
           if (int rc = set_smem(k_ident_bwd_w_long, smem)) return rc;
           MRGCN_PROF("ident_bwd_w_long");
-          k_ident_bwd_w_long<<<(unsigned)gI->n_long_cols, kThreads, smem, st>>>(f.comp_I, gI->long_cols, gI->colptr,
-                                                                                gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact,
-                                                                                a->g_weight_I, NS, B, out, EL);
+          k_ident_bwd_w_long<<<(unsigned)gI->n_long_cols, kHubThreads, smem, st>>>(
+              f.comp_I, gI->long_cols, gI->colptr, gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact, a->g_weight_I, NS, gI->R, B,
+              out, EL, comp_smem);
           MRGCN_LAUNCH_CHECK();
         }
       }
@@ -699,33 +606,18 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         MRGCN_REQUIRE(a->cbuf && a->part, MRGCN_E_BADARG, "layer_bwd: cbuf/part missing");
         if (gI->E > 0) {
           unsigned grid = 0;
-          const int TJb = ident_tile_bulk(NS, out);
-          int S = 0;
           size_t smem = 0;
-          int stage_floats = 0;
-          if (TJb > 0) {
-            stage_floats = ((B * TJb * out + 3) & ~3) + 16;
-            for (S = 4; S >= 2; --S) {
-              smem = 16 * ((S * 8 + 15) / 16) + (size_t)S * stage_floats * 4;
-              if (smem <= 100 * 1024) break;
-            }
-            if (S < 2)
-              for (S = 4; S >= 2; --S) {
-                smem = 16 * ((S * 8 + 15) / 16) + (size_t)S * stage_floats * 4;
-                if (smem <= 200 * 1024) break;
-              }
-          }
-          if (TJb > 0 && S >= 2) {
+          IdentPipe p;
+          if (ident_pipe_config(p, NS, B, out, 0)) {
             const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
-            const int ntiles = (int)cdiv(NS, TJb);
+            smem = 16 * ((2 * p.S * 8 + 15) / 16) + (size_t)p.S * p.stage_bytes;
             MRGCN_PROF("ident_bwd_c");
 #define LAUNCH(OCV, VWV)                                                                                          \
   do {                                                                                                            \
     if (int rc = set_smem(k_ident_bwd_c_bulk<OCV, VWV>, smem)) return rc;                                         \
-    grid = persistent_grid(k_ident_bwd_c_bulk<OCV, VWV>, kThreads, smem, ntiles);                                 \
-    k_ident_bwd_c_bulk<OCV, VWV><<<grid, kThreads, smem, st>>>(f.weight_I, gI->colptr, gI->e2_src, gI->e2_dst,    \
-                                                               gI->e2_val, a->gact, a->cbuf, (int)NS, B, out, TJb, \
-                                                               S, stage_floats, ntiles);                          \
+    grid = persistent_grid(k_ident_bwd_c_bulk<OCV, VWV>, kPipeThreads, smem, p.ntiles);                           \
+    k_ident_bwd_c_bulk<OCV, VWV><<<grid, kPipeThreads, smem, st>>>(f.weight_I, gI->colptr, gI->e2_src, gI->e2_dst, \
+                                                                   gI->e2_val, a->gact, a->cbuf, p);               \
   } while (0)
 #define LAUNCH_VW(OCV)                \
   do {                                \
@@ -769,7 +661,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
           MRGCN_LAUNCH_CHECK();
         }
         MRGCN_PROF("comp_reduce");
-        k_seq_reduce<<<dim3((unsigned)cdiv(B, 128), (unsigned)gI->R), 128, 0, st>>>(a->part, gI->rel_chunk_ptr,
+        k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)gI->R), 256, 0, st>>>(a->part, gI->rel_chunk_ptr,
                                                                                     gI->n_chunks, B, a->g_comp_I);
         MRGCN_LAUNCH_CHECK();
       }
@@ -797,7 +689,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         MRGCN_LAUNCH_CHECK();
       }
       MRGCN_PROF("feat_w_reduce");
-  k_seq_reduce<<<dim3((unsigned)cdiv(IO, 128), (unsigned)gF->R), 128, 0, st>>>(a->part, gF->rel_chunk_ptr,
+  k_seq_reduce<<<dim3((unsigned)cdiv(IO, 32), (unsigned)gF->R), 256, 0, st>>>(a->part, gF->rel_chunk_ptr,
                                                                                    gF->n_chunks, IO, gW);
       MRGCN_LAUNCH_CHECK();
       if (B > 0) {
@@ -814,25 +706,19 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       }
     }
     if (a->g_X) {
+      MRGCN_REQUIRE(a->wt_ws && a->msgx_ws, MRGCN_E_BADARG, "layer_bwd: wt_ws/msgx_ws missing");
       const int64_t NS = gF->NS;
-      const int thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
       if (NS > 0) {
-        const int TJ = in >= kThreads ? 1 : kThreads / in;
-        const int EC = pick_ec(out);
-        size_t smem = ((size_t)EC * out + EC) * 4;
-        MRGCN_REQUIRE(smem <= 200 * 1024, MRGCN_E_NOTSUP, "feat_bwd_x: out too large for shared memory");
-        if (int rc = set_smem(k_feat_bwd_x, smem)) return rc;
-        unsigned grid = persistent_grid(k_feat_bwd_x, kThreads, smem, cdiv(NS, TJ));
-        MRGCN_PROF("feat_bwd_x");
-        k_feat_bwd_x<<<grid, kThreads, smem, st>>>(W, gF->colptr, gF->e2_dst, gF->e2_rel, gF->e2_val, a->gact, a->g_X,
-                                                   (int)NS, in, out, TJ, thresh, EC);
+        MRGCN_PROF("transpose_w");
+        k_transpose_w<<<dim3((unsigned)cdiv(IO, 128), (unsigned)gF->R), 128, 0, st>>>(W, a->wt_ws, in, out);
         MRGCN_LAUNCH_CHECK();
-        if (gF->n_long_cols > 0) {
-          MRGCN_PROF("feat_bwd_x_long");
-          k_feat_bwd_x_long<<<(unsigned)gF->n_long_cols, kThreads, 0, st>>>(W, gF->long_cols, gF->colptr, gF->e2_dst, gF->e2_rel,
-                                                                            gF->e2_val, a->gact, a->g_X, in, out);
-          MRGCN_LAUNCH_CHECK();
-        }
+        if (gF->E > 0)
+          if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
+        AggArgs g{};
+        g.ND = (int)NS; g.odim = in; g.out = a->g_X;
+        g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;
+        g.thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
+        if (int rc = launch_agg(g, gF->long_cols, gF->n_long_cols, st, "feat_bwd_x_agg")) return rc;
       }
     }
   }

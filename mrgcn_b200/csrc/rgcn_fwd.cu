@@ -14,6 +14,8 @@
 // All passes are HBM/L2-bound gathers; there is no float atomic anywhere.
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "ident_pipe.cuh"
+#include "rgcn_internal.cuh"
 
 namespace mrgcn {
 namespace {
@@ -98,54 +100,43 @@ __device__ __forceinline__ void load_comp_smem(float *comp_s, const float *__res
     for (int b = threadIdx.x & 31; b < B; b += 32) comp_s[r * CS + b] = __ldg(comp + (size_t)r * B + b);
 }
 
-// (a) TMA-engine variant: every basis run of the tile is one cp.async.bulk into a ring of S stages, completion on
-//     an mbarrier per stage; thread 0 is the producer, all threads consume.  Needs 16-byte aligned runs:
-//     (NS*out) % 4 == 0, (TJ*out) % 4 == 0, NS >= TJ.  The last tile is shifted back to NS-TJ so that every tile
-//     is full; the sources it shares with its predecessor produce identical messages twice.
+// (a) TMA-engine variant (ident_pipe.cuh): producer warp + ring of stages + consumer warps; needs 16-byte aligned
+//     runs: (NS*out) % 4 == 0, (TJ*out) % 4 == 0, NS >= TJ.  The last tile is shifted back to NS-TJ so that every
+//     tile is full; the sources it shares with its predecessor produce identical messages twice.
 template <int OC, int VW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPipeThreads)
 k_ident_msg_fwd_bulk(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
                      const int32_t *__restrict__ e2_src, const int32_t *__restrict__ e2_rel,
-                     const float *__restrict__ e2_val, float *__restrict__ msg, int NS, int R, int B, int out, int TJ,
-                     int CS, int comp_smem, int S, int stage_floats, int ntiles) {
+                     const float *__restrict__ e2_val, float *__restrict__ msg, IdentPipe p, int R, int CS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-  float *comp_s = reinterpret_cast<float *>(smem_raw + 16 * ((S * 8 + 15) / 16));
-  float *stages = comp_s + (comp_smem ? ((R * CS + 3) & ~3) : 0);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *empty = full + p.S;
+  float *comp_s = reinterpret_cast<float *>(smem_raw + 16 * ((2 * p.S * 8 + 15) / 16));
+  unsigned char *stages = reinterpret_cast<unsigned char *>(comp_s + ((R * CS + 3) & ~3));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kPipeConsumerWarps); }
     mbar_fence_init();
   }
-  if (comp_smem) load_comp_smem(comp_s, comp, R, B, CS);
+  for (int r = threadIdx.x / 32; r < R; r += kPipeThreads / 32)
+    for (int b = threadIdx.x & 31; b < p.B; b += 32) comp_s[r * CS + b] = __ldg(comp + (size_t)r * p.B + b);
   __syncthreads();
-  const uint32_t run_bytes = (uint32_t)TJ * out * 4;
-  auto issue = [&](int k) {
-    const int t = blockIdx.x + k * gridDim.x;
-    if (t >= ntiles) return;
-    const int s = k % S;
-    int j0 = t * TJ;
-    if (j0 + TJ > NS) j0 = NS - TJ;
-    float *dst = stages + (size_t)s * stage_floats;
-    fence_proxy_async();
-    mbar_expect_tx(&bars[s], run_bytes * B);
-    for (int b = 0; b < B; ++b)
-      bulk_g2s(dst + (size_t)b * TJ * out, V + ((size_t)b * NS + j0) * out, run_bytes, &bars[s]);
-  };
-  if (tid == 0)
-    for (int k = 0; k < S - 1; ++k) issue(k);
-  for (int k = 0;; ++k) {
-    const int t = blockIdx.x + k * gridDim.x;
-    if (t >= ntiles) break;
-    if (tid == 0) issue(k + S - 1);
-    int j0 = t * TJ;
-    if (j0 + TJ > NS) j0 = NS - TJ;
-    const int e_lo = colptr[j0], e_hi = colptr[j0 + TJ];
-    mbar_wait(&bars[k % S], (k / S) & 1);
-    ident_msg_tile<OC, VW>(stages + (size_t)(k % S) * stage_floats, (size_t)TJ * out, out, comp_smem ? comp_s : nullptr, CS,
-                           comp, B, out, j0, e_lo, e_hi, e2_src, e2_rel, e2_val, msg);
-    __syncthreads();  // stage (k % S) may be refilled by the producer in the next iteration
-  }
+  const int B = p.B, out = p.out;
+  const size_t bstride = (size_t)p.TJ * out;
+  ident_pipeline(p, V, colptr, e2_src, e2_rel, e2_val, stages, full, empty,
+                 [&](const float *vs, int j0, int e, int src, int rel, float v) {
+                   const float *cr = comp_s + rel * CS;
+                   const float *vrow = vs + (size_t)(src - j0) * out;
+                   for (int c0 = 0; c0 < out; c0 += OC) {
+                     float acc[OC];
+#pragma unroll
+                     for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+                     mix_bases<OC, VW>(vrow + c0, bstride, cr, B, acc);
+                     float *mp = msg + (size_t)e * out + c0;
+#pragma unroll
+                     for (int o = 0; o < OC; ++o)
+                       if (c0 + o < out) mp[o] = v * acc[o];
+                   }
+                 });
 }
 
 // (b) generic variant (any alignment): cooperative coalesced loads into a padded tile.
@@ -197,7 +188,7 @@ template <int OC>
 __global__ void __launch_bounds__(kThreads)
 k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const int32_t *__restrict__ chunk_rel,
                const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ e3_src,
-               const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {
+               const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {  // e3_src: gather index
   extern __shared__ __align__(16) float smem[];
   float *Ws = smem;                         // [INP][OC]
   float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][2][32][KC+1]
@@ -274,22 +265,7 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Aggregation over destination rows (E1), fused with bias, row mask and ReLU.
-struct AggArgs {
-  const int32_t *rowptr;
-  const int32_t *pI;   // e1_to_e2 of gI (messages of the identity term) or NULL
-  const float *msgI;
-  const int32_t *pF;   // e1_to_e3 of gF or NULL
-  const float *msgF;
-  const int32_t *rowptrF;  // rowptr of gF (== rowptr when gI == gF)
-  const float *Wd;     // weight_I for the direct gather (B == 0) or NULL
-  const int32_t *d_src, *d_rel;
-  const float *d_val;
-  int64_t NSd;
-  const float *bias, *mask, *addend;
-  float *out;
-  int ND, odim, relu, thresh;
-};
+// Aggregation over destination rows (E1), fused with bias, row mask and ReLU (AggArgs: rgcn_internal.cuh).
 
 // sum of msg[perm[e]][o] over e = lo+beg, lo+beg+step, ... < hi; four gathers in flight, fixed order
 __device__ __forceinline__ float gather_sum(const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi,
@@ -360,12 +336,13 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
 }
 
 // long rows (hubs): one CTA per row, edge slots strided over the row, fixed-order tree over slots
-__global__ void __launch_bounds__(kThreads) k_agg_fwd_long(AggArgs a, const int32_t *__restrict__ long_rows) {
+constexpr int kLongThreads = 1024;
+__global__ void __launch_bounds__(kLongThreads) k_agg_fwd_long(AggArgs a, const int32_t *__restrict__ long_rows) {
   extern __shared__ float red[];  // [nslots][oc]
   const int od = a.odim;
   const int i = long_rows[blockIdx.x];
-  const int oc = min(od, kThreads);
-  const int nslots = kThreads / oc;
+  const int oc = min(od, kLongThreads);
+  const int nslots = kLongThreads / oc;
   const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
   for (int o0 = 0; o0 < od; o0 += oc) {
     const int o = o0 + ol;
@@ -417,15 +394,22 @@ int ident_tile(int B, int out, int OP) {
   return tj;
 }
 
-// tile of the TMA-engine variants: largest TJ with TJ*out <= 256 floats and 16-byte runs; 0 = not applicable
-int ident_tile_bulk(int64_t NS, int out) {
+// tile of the TMA-engine variants: ~48 KB of V per stage, 16-byte runs; 0 = not applicable
+int ident_tile_bulk(int64_t NS, int out) { return (NS * out) % 4 == 0 ? 1 : 0; }
+int ident_pipe_config(IdentPipe &p, int64_t NS, int B, int out, size_t other_smem) {
   if ((NS * out) % 4 != 0) return 0;
-  int tj = 256 / out;
-  if (tj < 1) tj = 1;
+  int tj = (48 * 1024) / (B * out * 4);
+  if (tj > 64) tj = 64;
   while (tj > 0 && (tj * out) % 4 != 0) --tj;
-  if (tj <= 0 && (out % 4) == 0) tj = 1;
   if (tj <= 0 || tj > NS) return 0;
-  return tj;
+  p.NS = (int)NS; p.B = B; p.out = out; p.TJ = tj;
+  p.ntiles = (int)cdiv(NS, tj);
+  p.mcap = 1024;
+  p.v_floats = ((B * tj * out + 3) & ~3) + 16;
+  p.stage_bytes = ident_pipe_stage_bytes(p.v_floats, p.mcap);
+  for (p.S = 4; p.S >= 2; --p.S)
+    if (16 * ((2 * p.S * 8 + 15) / 16) + other_smem + (size_t)p.S * p.stage_bytes <= 200 * 1024) return 1;
+  return 0;
 }
 
 static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const float *comp, float *msg, int B, int out,
@@ -435,44 +419,34 @@ static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const floa
   const int comp_smem = ((size_t)g->R * CS * 4 <= 64 * 1024) ? 1 : 0;
   const size_t comp_bytes = (comp_smem ? (((size_t)g->R * CS + 3) & ~(size_t)3) : 0) * 4;
   unsigned grid = 0;
-  const int TJb = ident_tile_bulk(g->NS, out);
-  if (TJb > 0) {
+  IdentPipe p;
+  if (comp_smem && ident_pipe_config(p, g->NS, B, out, comp_bytes)) {
     const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
-    const int stage_floats = ((B * TJb * out + 3) & ~3) + 16;
-    int S = 4;
-    size_t smem = 0;
-    for (; S >= 2; --S) {
-      smem = 16 * ((S * 8 + 15) / 16) + comp_bytes + (size_t)S * stage_floats * 4;
-      if (smem <= 200 * 1024) break;
+    const size_t smem = 16 * ((2 * p.S * 8 + 15) / 16) + comp_bytes + (size_t)p.S * p.stage_bytes;
+    MRGCN_PROF("ident_msg_fwd");
+#define LAUNCH(OCV, VWV)                                                                                            \
+  do {                                                                                                              \
+    if (int rc = set_smem(k_ident_msg_fwd_bulk<OCV, VWV>, smem)) return rc;                                         \
+    grid = persistent_grid(k_ident_msg_fwd_bulk<OCV, VWV>, kPipeThreads, smem, p.ntiles);                           \
+    k_ident_msg_fwd_bulk<OCV, VWV><<<grid, kPipeThreads, smem, st>>>(V, comp, g->colptr, g->e2_src, g->e2_rel,     \
+                                                                     g->e2_val, msg, p, g->R, CS);                  \
+  } while (0)
+#define LAUNCH_VW(OCV)                \
+  do {                                \
+    if (VW == 4) LAUNCH(OCV, 4);      \
+    else if (VW == 2) LAUNCH(OCV, 2); \
+    else LAUNCH(OCV, 1);              \
+  } while (0)
+    switch (OC) {
+      case 4: LAUNCH_VW(4); break;
+      case 8: LAUNCH_VW(8); break;
+      case 12: LAUNCH_VW(12); break;
+      default: LAUNCH_VW(16); break;
     }
-    if (S >= 2) {
-      const int ntiles = (int)cdiv(g->NS, TJb);
-      MRGCN_PROF("ident_msg_fwd");
-#define LAUNCH(OCV, VWV)                                                                                           \
-  do {                                                                                                             \
-    if (int rc = set_smem(k_ident_msg_fwd_bulk<OCV, VWV>, smem)) return rc;                                        \
-    grid = persistent_grid(k_ident_msg_fwd_bulk<OCV, VWV>, kThreads, smem, ntiles);                                \
-    k_ident_msg_fwd_bulk<OCV, VWV><<<grid, kThreads, smem, st>>>(V, comp, g->colptr, g->e2_src, g->e2_rel, g->e2_val, \
-                                                                 msg, g->NS, g->R, B, out, TJb, CS, comp_smem, S,  \
-                                                                 stage_floats, ntiles);                            \
-  } while (0)
-#define LAUNCH_VW(OCV)                                   \
-  do {                                                   \
-    if (VW == 4) LAUNCH(OCV, 4);                         \
-    else if (VW == 2) LAUNCH(OCV, 2);                    \
-    else LAUNCH(OCV, 1);                                 \
-  } while (0)
-      switch (OC) {
-        case 4: LAUNCH_VW(4); break;
-        case 8: LAUNCH_VW(8); break;
-        case 12: LAUNCH_VW(12); break;
-        default: LAUNCH_VW(16); break;
-      }
 #undef LAUNCH_VW
 #undef LAUNCH
-      MRGCN_LAUNCH_CHECK();
-      return 0;
-    }
+    MRGCN_LAUNCH_CHECK();
+    return 0;
   }
   const int OP = (int)cdiv(out, OC) * OC;
   const int TJ = ident_tile(B, out, OP);
@@ -497,20 +471,20 @@ static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const floa
   return 0;
 }
 
-static int launch_feat_msg_fwd(const mrgcn_graph *g, const float *X, const float *W, float *msg, int in, int out,
-                               cudaStream_t st) {
+int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
+                    int out, cudaStream_t st, const char *prof_name) {
   if (g->n_chunks == 0) return 0;
   const int OC = pick_oc(out);
   const int INP = (int)cdiv(in, KC) * KC;
   size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 2 * 32 * (KC + 1)) * 4;
-  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "feat_msg_fwd: in too large for shared memory (%zu B)", smem);
+  MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "feat_msg: in too large for shared memory (%zu B)", smem);
 #define LAUNCH(OCV)                                                                                            \
   do {                                                                                                         \
     if (int rc = set_smem(k_feat_msg_fwd<OCV>, smem)) return rc;                                               \
     k_feat_msg_fwd<OCV><<<(unsigned)g->n_chunks, kThreads, smem, st>>>(X, W, g->chunk_rel, g->chunk_ptr,      \
-                                                                      g->e3_src, g->e3_val, msg, in, out, INP); \
+                                                                      gather, g->e3_val, msg, in, out, INP);  \
   } while (0)
-  MRGCN_PROF("feat_msg_fwd");
+  mrgcn::prof_begin(prof_name, st);
   switch (OC) {
     case 4: LAUNCH(4); break;
     case 8: LAUNCH(8); break;
@@ -519,6 +493,21 @@ static int launch_feat_msg_fwd(const mrgcn_graph *g, const float *X, const float
   }
 #undef LAUNCH
   MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_agg(const AggArgs &g, const int32_t *long_rows, int n_long, cudaStream_t st, const char *prof_name) {
+  if (g.ND <= 0) return 0;
+  const int rows_per_warp = g.odim >= 32 ? 1 : 32 / g.odim;
+  unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
+  mrgcn::prof_begin(prof_name, st);
+  k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
+  MRGCN_LAUNCH_CHECK();
+  if (n_long > 0) {
+    mrgcn::prof_begin("agg_long", st);
+    k_agg_fwd_long<<<(unsigned)n_long, kLongThreads, kLongThreads * sizeof(float), st>>>(g, long_rows);
+    MRGCN_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -561,22 +550,11 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
     }
     MRGCN_REQUIRE(a->msg_F, MRGCN_E_BADARG, "layer_fwd: msg_F missing");
     if (gF->E > 0)
-      if (int rc = launch_feat_msg_fwd(gF, a->X, W, a->msg_F, in, out, st)) return rc;
+      if (int rc = launch_feat_msg(gF, gF->e3_src, a->X, W, a->msg_F, in, out, st, "feat_msg_fwd")) return rc;
     g.pF = gF->e1_to_e3; g.msgF = a->msg_F; g.rowptrF = gF->rowptr;
   }
   // long rows are those of either graph; the host side builds the union list on the owner graph
   g.thresh = gl->n_long_rows > 0 ? gl->long_row_thresh : 0;
-  const int rows_per_warp = out >= 32 ? 1 : 32 / out;
-  unsigned grid = (unsigned)cdiv(cdiv(ND, rows_per_warp) * 32, kThreads);
-  if (ND > 0) {
-    MRGCN_PROF("agg_fwd");
-  k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
-    MRGCN_LAUNCH_CHECK();
-    if (gl->n_long_rows > 0) {
-      MRGCN_PROF("agg_fwd_long");
-  k_agg_fwd_long<<<(unsigned)gl->n_long_rows, kThreads, kThreads * sizeof(float), st>>>(g, gl->long_rows);
-      MRGCN_LAUNCH_CHECK();
-    }
-  }
+  if (int rc = launch_agg(g, gl->long_rows, gl->n_long_rows, st, "agg_fwd")) return rc;
   return 0;
 }

@@ -1,0 +1,35 @@
+// Internal launch helpers shared by rgcn_fwd.cu and rgcn_bwd.cu.
+#pragma once
+#include "common.cuh"
+
+namespace mrgcn {
+
+// Arguments of the segmented message aggregation (rows = destinations in forward, sources in the input-gradient pass).
+struct AggArgs {
+  const int32_t *rowptr;
+  const int32_t *pI;   // e1_to_e2 of gI (messages of the identity term) or NULL
+  const float *msgI;
+  const int32_t *pF;   // e1_to_e3 of gF or NULL
+  const float *msgF;
+  const int32_t *rowptrF;  // rowptr of gF (== rowptr when gI == gF)
+  const float *Wd;     // weight_I for the direct gather (B == 0) or NULL
+  const int32_t *d_src, *d_rel;
+  const float *d_val;
+  int64_t NSd;
+  const float *bias, *mask, *addend;
+  float *out;
+  int ND, odim, relu, thresh;
+};
+
+int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st);
+// msg[e3,:] = val_e * Xrows[gather[e3], :] . W[r]   (gather = e3_src forward, e3_dst for the input gradient)
+int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
+                    int out, cudaStream_t st, const char *prof_name);
+// segmented sums of AggArgs over n_rows rows (+ hub rows listed in long_rows)
+int launch_agg(const AggArgs &a, const int32_t *long_rows, int n_long, cudaStream_t st, const char *prof_name);
+int pick_oc(int out);
+int ident_tile(int B, int out, int OP);
+struct IdentPipe;
+int ident_pipe_config(IdentPipe &p, int64_t NS, int B, int out, size_t other_smem);
+
+}  // namespace mrgcn

@@ -33,13 +33,14 @@ class RelGraph:
 
     def __init__(self, E, ND, NS, R, device):
         self.E, self.ND, self.NS, self.R, self.device = int(E), int(ND), int(NS), int(R), device
-        e = max(self.E, 1)
+        e = self.E + 8          # slack: the TMA-engine kernels copy edge ranges rounded up to 16 bytes
         mk_i = lambda n: torch.empty(n, dtype=_I32, device=device)
         mk_f = lambda n: torch.empty(n, dtype=torch.float32, device=device)
         self.rowptr, self.colptr, self.relptr = mk_i(ND + 1), mk_i(NS + 1), mk_i(R + 1)
         self.e1_src, self.e1_rel, self.e1_val = mk_i(e), mk_i(e), mk_f(e)
         self.e1_to_e2, self.e1_to_e3 = mk_i(e), mk_i(e)
         self.e2_src, self.e2_dst, self.e2_rel, self.e2_val = mk_i(e), mk_i(e), mk_i(e), mk_f(e)
+        self.e2_to_e3 = mk_i(e)
         self.e3_src, self.e3_dst, self.e3_val, self.e3_to_e2 = mk_i(e), mk_i(e), mk_f(e), mk_i(e)
         self.long_rows = self.long_cols = None
         self.chunk_rel = self.chunk_ptr = self.rel_chunk_ptr = None
@@ -51,7 +52,7 @@ class RelGraph:
         c = self.c
         c.E, c.ND, c.NS, c.R = self.E, self.ND, self.NS, self.R
         for name in ("rowptr", "e1_src", "e1_rel", "e1_val", "e1_to_e2", "e1_to_e3", "colptr", "e2_src", "e2_dst",
-                     "e2_rel", "e2_val", "relptr", "e3_src", "e3_dst", "e3_val", "e3_to_e2"):
+                     "e2_rel", "e2_val", "e2_to_e3", "relptr", "e3_src", "e3_dst", "e3_val", "e3_to_e2"):
             setattr(c, name, getattr(self, name).data_ptr())
 
     def _build_worklists(self, chunk=None):

@@ -95,8 +95,11 @@ class _LayerFn(torch.autograd.Function):
             if B:
                 g_cF = torch.empty_like(comp_F)
                 g_wmix = _empty(gF.R * in_dim * out_dim, dev)
+        wt_ws = msgx_ws = None
         if hasF and need[0]:
             g_X = torch.empty_like(X)
+            wt_ws = _empty(gF.R * in_dim * out_dim, dev)
+            msgx_ws = _empty(gF.E * in_dim, dev)
         colsum = None
         if bias is not None and need[5]:
             g_b = torch.empty_like(bias)
@@ -106,6 +109,7 @@ class _LayerFn(torch.autograd.Function):
         b.g_weight_I, b.g_comp_I, b.g_weight_F, b.g_comp_F = nv.ptr(g_wI), nv.ptr(g_cI), nv.ptr(g_wF), nv.ptr(g_cF)
         b.g_bias, b.g_X = nv.ptr(g_b), nv.ptr(g_X)
         b.gact, b.cbuf, b.part, b.g_wmix, b.colsum_ws = nv.ptr(gact), nv.ptr(cbuf), nv.ptr(part), nv.ptr(g_wmix), nv.ptr(colsum)
+        b.wt_ws, b.msgx_ws = nv.ptr(wt_ws), nv.ptr(msgx_ws)
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
         g_add = gact[:g0.ND * out_dim].view(g0.ND, out_dim) if (ctx.has_addend and need[11]) else None
