@@ -75,6 +75,12 @@ typedef struct mrgcn_graph {
   /* work lists (built by the host side from rowptr/colptr/relptr) */
   int32_t *long_rows;  int32_t n_long_rows;  int32_t long_row_thresh;   /* rows with deg > thresh */
   int32_t *long_cols;  int32_t n_long_cols;  int32_t long_col_thresh;
+  /* hubs are cut into segments of long_seg edges, one CTA each; partial sums are combined in segment order */
+  int32_t *row_seg_hub;   /* [n_row_segs] index into long_rows */
+  int32_t *row_seg_first; /* [n_long_rows+1] first segment of hub h */
+  int32_t *col_seg_hub;   /* [n_col_segs] */
+  int32_t *col_seg_first; /* [n_long_cols+1] */
+  int32_t n_row_segs, n_col_segs, long_seg, _pad3;
   int32_t *chunk_rel;  /* [n_chunks] relation of E3 chunk c */
   int32_t *chunk_ptr;  /* [n_chunks+1] E3 edge range of chunk c (never crosses a relation) */
   int32_t *rel_chunk_ptr; /* [R+1] chunk range of relation r */
@@ -123,6 +129,7 @@ typedef struct mrgcn_layer_args {
   int32_t in_dim, out_dim, B, relu;
   const float *weight_I, *comp_I, *X, *weight_F, *comp_F, *bias, *row_mask, *addend;
   float *wmix, *msg_I, *msg_F;
+  float *hub_ws; /* [max(n_row_segs, n_col_segs) * max(out, in, B*out)] partial sums of hub segments (may be NULL without hubs) */
   float *out; /* [ND, out] */
 } mrgcn_layer_args;
 int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);

@@ -29,6 +29,9 @@ class Graph(C.Structure):
         ("e3_to_e2", C.c_void_p),
         ("long_rows", C.c_void_p), ("n_long_rows", C.c_int32), ("long_row_thresh", C.c_int32),
         ("long_cols", C.c_void_p), ("n_long_cols", C.c_int32), ("long_col_thresh", C.c_int32),
+        ("row_seg_hub", C.c_void_p), ("row_seg_first", C.c_void_p), ("col_seg_hub", C.c_void_p),
+        ("col_seg_first", C.c_void_p), ("n_row_segs", C.c_int32), ("n_col_segs", C.c_int32), ("long_seg", C.c_int32),
+        ("_pad3", C.c_int32),
         ("chunk_rel", C.c_void_p), ("chunk_ptr", C.c_void_p), ("rel_chunk_ptr", C.c_void_p),
         ("n_chunks", C.c_int32), ("_pad2", C.c_int32),
     ]
@@ -41,7 +44,7 @@ class LayerArgs(C.Structure):
         ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("B", C.c_int32), ("relu", C.c_int32),
         ("weight_I", C.c_void_p), ("comp_I", C.c_void_p), ("X", C.c_void_p), ("weight_F", C.c_void_p),
         ("comp_F", C.c_void_p), ("bias", C.c_void_p), ("row_mask", C.c_void_p), ("addend", C.c_void_p),
-        ("wmix", C.c_void_p), ("msg_I", C.c_void_p), ("msg_F", C.c_void_p),
+        ("wmix", C.c_void_p), ("msg_I", C.c_void_p), ("msg_F", C.c_void_p), ("hub_ws", C.c_void_p),
         ("out", C.c_void_p),
     ]
 

@@ -338,34 +338,43 @@ k_ident_bwd_w_generic(const float *__restrict__ comp, const int32_t *__restrict_
   }
 }
 
-// hubs: one CTA (1024 threads) per long source.  Rounds of EL edges are staged like above; comp is resident in
-// shared memory; thread p owns the (basis, o) pairs p, p + 1024, ... and walks the staged edges in order.
+// hubs: one CTA (1024 threads) per SEGMENT of a long source (HubSegs).  The segment's edges are staged like above; comp
+// is resident in shared memory; thread p owns the (basis, o) pairs p, p + 1024, ... and walks the staged edges in order.
+// A single-segment hub is finished here; otherwise the partial goes to ws[seg] for k_ident_bwd_w_combine.
 constexpr int kHubThreads = 1024;
 __global__ void __launch_bounds__(kHubThreads)
-k_ident_bwd_w_long(const float *__restrict__ comp, const int32_t *__restrict__ long_cols,
-                   const int32_t *__restrict__ colptr, const int32_t *__restrict__ e2_dst,
-                   const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
-                   const float *__restrict__ gact, float *__restrict__ gW, int64_t NS, int R, int B, int out, int EL,
-                   int comp_smem) {
+k_ident_bwd_w_long(const float *__restrict__ comp, HubSegs h, const int32_t *__restrict__ colptr,
+                   const int32_t *__restrict__ e2_dst, const int32_t *__restrict__ e2_rel,
+                   const float *__restrict__ e2_val, const float *__restrict__ gact, float *__restrict__ gW, int64_t NS,
+                   int R, int B, int out, int comp_smem, int EL) {
   extern __shared__ __align__(16) float smem[];
   float *Ts = smem;                                          // [EL][out]
   int *Rs = reinterpret_cast<int *>(Ts + (size_t)EL * out);  // [EL]  (pre-multiplied by B)
   float *comp_s = reinterpret_cast<float *>(Rs + EL);        // [R][B]
-  const int j = long_cols[blockIdx.x];
-  const int e_lo = colptr[j], e_hi = colptr[j + 1];
+  const int sg = blockIdx.x;
+  const int hub = h.seg_hub[sg];
+  const int j = h.long_ids[hub];
+  const int first = h.seg_first[hub], nseg = h.seg_first[hub + 1] - first;
+  const int s_lo = min(colptr[j + 1], colptr[j] + (sg - first) * h.seg);
+  const int s_hi = min(colptr[j + 1], s_lo + h.seg);
   const int tid = threadIdx.x;
   if (comp_smem)
     for (int x = tid; x < R * B; x += kHubThreads) comp_s[x] = __ldg(comp + x);
   const float *cbase = comp_smem ? comp_s : comp;
   const int npairs = B * out;
-  for (int p0 = 0; p0 < npairs; p0 += 2 * kHubThreads) {
-    float acc0 = 0.f, acc1 = 0.f;
-    const int pa = p0 + tid, pb = p0 + kHubThreads + tid;
-    const bool va = pa < npairs, vb = pb < npairs;
-    const int ba = va ? pa / out : 0, oa = va ? pa - ba * out : 0;
-    const int bb = vb ? pb / out : 0, ob = vb ? pb - bb * out : 0;
-    for (int c_lo = e_lo; c_lo < e_hi; c_lo += EL) {
-      const int n = min(EL, e_hi - c_lo);
+  constexpr int PP = 4;  // pairs per thread per pass
+  for (int p0 = 0; p0 < npairs; p0 += PP * kHubThreads) {
+    float acc[PP];
+    int pb[PP], po[PP];
+#pragma unroll
+    for (int q = 0; q < PP; ++q) {
+      const int p = p0 + q * kHubThreads + tid;
+      acc[q] = 0.f;
+      pb[q] = p < npairs ? p / out : -1;
+      po[q] = p < npairs ? p - pb[q] * out : 0;
+    }
+    for (int c_lo = s_lo; c_lo < s_hi; c_lo += EL) {
+      const int n = min(EL, s_hi - c_lo);
       __syncthreads();
       for (int el = tid; el < n; el += kHubThreads) {
         const int e = c_lo + el;
@@ -375,17 +384,38 @@ k_ident_bwd_w_long(const float *__restrict__ comp, const int32_t *__restrict__ l
         for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
       }
       __syncthreads();
-      if (va) {
-#pragma unroll 4
-        for (int el = 0; el < n; ++el) {
-          const float *cr = cbase + Rs[el];
-          acc0 = fmaf(cr[ba], Ts[el * out + oa], acc0);
-          if (vb) acc1 = fmaf(cr[bb], Ts[el * out + ob], acc1);
+#pragma unroll
+      for (int q = 0; q < PP; ++q) {
+        if (pb[q] < 0) continue;
+        float a0 = 0.f, a1 = 0.f;
+        int el = 0;
+        for (; el + 1 < n; el += 2) {
+          a0 = fmaf(cbase[Rs[el] + pb[q]], Ts[el * out + po[q]], a0);
+          a1 = fmaf(cbase[Rs[el + 1] + pb[q]], Ts[(el + 1) * out + po[q]], a1);
         }
+        if (el < n) a0 = fmaf(cbase[Rs[el] + pb[q]], Ts[el * out + po[q]], a0);
+        acc[q] += a0 + a1;
       }
     }
-    if (va) gW[((size_t)ba * NS + j) * out + oa] = acc0;
-    if (vb) gW[((size_t)bb * NS + j) * out + ob] = acc1;
+#pragma unroll
+    for (int q = 0; q < PP; ++q) {
+      if (pb[q] < 0) continue;
+      if (nseg == 1) gW[((size_t)pb[q] * NS + j) * out + po[q]] = acc[q];
+      else h.ws[(size_t)sg * npairs + (size_t)pb[q] * out + po[q]] = acc[q];
+    }
+  }
+}
+__global__ void k_ident_bwd_w_combine(HubSegs h, float *__restrict__ gW, int64_t NS, int B, int out) {
+  const int hub = blockIdx.x;
+  const int first = h.seg_first[hub], nseg = h.seg_first[hub + 1] - first;
+  if (nseg <= 1) return;
+  const int j = h.long_ids[hub];
+  const int npairs = B * out;
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < nseg; ++s) acc += h.ws[(size_t)(first + s) * npairs + p];
+    const int b = p / out, o = p - b * out;
+    gW[((size_t)b * NS + j) * out + o] = acc;
   }
 }
 
@@ -591,15 +621,23 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         }
         if (gI->n_long_cols > 0) {
           const int comp_smem = (size_t)gI->R * B * 4 <= 64 * 1024 ? 1 : 0;
-          int EL = 1024;
+          HubSegs hs{gI->long_cols, gI->col_seg_hub, gI->col_seg_first, gI->n_long_cols, gI->n_col_segs, gI->long_seg, f.hub_ws};
+          MRGCN_REQUIRE(hs.ws || hs.n_segs == hs.n_long, MRGCN_E_BADARG, "ident_bwd_w: hub_ws missing");
+          int EL = hs.seg;
           while (EL > 32 && ((size_t)EL * out + EL) * 4 > 64 * 1024) EL >>= 1;
           size_t smem = ((size_t)EL * out + EL + (comp_smem ? (size_t)gI->R * B : 0)) * 4;
+          MRGCN_REQUIRE(smem <= 200 * 1024, MRGCN_E_NOTSUP, "ident_bwd_w_long: out too large for shared memory");
           if (int rc = set_smem(k_ident_bwd_w_long, smem)) return rc;
           MRGCN_PROF("ident_bwd_w_long");
-          k_ident_bwd_w_long<<<(unsigned)gI->n_long_cols, kHubThreads, smem, st>>>(
-              f.comp_I, gI->long_cols, gI->colptr, gI->e2_dst, gI->e2_rel, gI->e2_val, a->gact, a->g_weight_I, NS, gI->R, B,
-              out, EL, comp_smem);
+          k_ident_bwd_w_long<<<(unsigned)hs.n_segs, kHubThreads, smem, st>>>(f.comp_I, hs, gI->colptr, gI->e2_dst, gI->e2_rel,
+                                                                            gI->e2_val, a->gact, a->g_weight_I, NS, gI->R, B,
+                                                                            out, comp_smem, EL);
           MRGCN_LAUNCH_CHECK();
+          if (hs.n_segs > hs.n_long) {
+            MRGCN_PROF("ident_bwd_w_combine");
+            k_ident_bwd_w_combine<<<(unsigned)hs.n_long, 256, 0, st>>>(hs, a->g_weight_I, NS, B, out);
+            MRGCN_LAUNCH_CHECK();
+          }
         }
       }
       if (a->g_comp_I) {
@@ -718,7 +756,8 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         g.ND = (int)NS; g.odim = in; g.out = a->g_X;
         g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;
         g.thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
-        if (int rc = launch_agg(g, gF->long_cols, gF->n_long_cols, st, "feat_bwd_x_agg")) return rc;
+        HubSegs hs{gF->long_cols, gF->col_seg_hub, gF->col_seg_first, gF->n_long_cols, gF->n_col_segs, gF->long_seg, f.hub_ws};
+        if (int rc = launch_agg(g, hs, st, "feat_bwd_x_agg")) return rc;
       }
     }
   }

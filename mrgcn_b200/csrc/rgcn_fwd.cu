@@ -281,22 +281,30 @@ __device__ __forceinline__ float gather_sum(const float *__restrict__ msg, const
   return acc;
 }
 
-__device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int beg, int step) {
+// sum over the sub-range [off, off+len) of row i's edges (len < 0: whole row), slots beg, beg+step, ...
+__device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int beg, int step, int off = 0, int len = -1) {
   float acc = 0.f;
   const int od = a.odim;
-  const int lo = a.rowptr ? a.rowptr[i] : 0, hi = a.rowptr ? a.rowptr[i + 1] : 0;
-  if (a.msgI) acc = gather_sum(a.msgI, a.pI, lo, hi, beg, step, od, o, acc);
-  if (a.Wd) {
-    int e = lo + beg;
-    for (; e + step < hi; e += 2 * step) {
-      const float w0 = a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o];
-      const float w1 = a.Wd[((size_t)a.d_rel[e + step] * a.NSd + a.d_src[e + step]) * od + o];
-      acc = fmaf(a.d_val[e], w0, acc);
-      acc = fmaf(a.d_val[e + step], w1, acc);
+  if (a.rowptr) {
+    int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+    if (len >= 0) { lo = min(hi, lo + off); hi = min(hi, lo + len); }
+    if (a.msgI) acc = gather_sum(a.msgI, a.pI, lo, hi, beg, step, od, o, acc);
+    if (a.Wd) {
+      int e = lo + beg;
+      for (; e + step < hi; e += 2 * step) {
+        const float w0 = a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o];
+        const float w1 = a.Wd[((size_t)a.d_rel[e + step] * a.NSd + a.d_src[e + step]) * od + o];
+        acc = fmaf(a.d_val[e], w0, acc);
+        acc = fmaf(a.d_val[e + step], w1, acc);
+      }
+      for (; e < hi; e += step) acc = fmaf(a.d_val[e], a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o], acc);
     }
-    for (; e < hi; e += step) acc = fmaf(a.d_val[e], a.Wd[((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o], acc);
   }
-  if (a.msgF) acc = gather_sum(a.msgF, a.pF, a.rowptrF[i], a.rowptrF[i + 1], beg, step, od, o, acc);
+  if (a.msgF) {
+    int lo = a.rowptrF[i], hi = a.rowptrF[i + 1];
+    if (len >= 0) { lo = min(hi, lo + off); hi = min(hi, lo + len); }
+    acc = gather_sum(a.msgF, a.pF, lo, hi, beg, step, od, o, acc);
+  }
   return acc;
 }
 
@@ -335,27 +343,46 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
   }
 }
 
-// long rows (hubs): one CTA per row, edge slots strided over the row, fixed-order tree over slots
+// hubs: one CTA (1024 threads) per SEGMENT of a long row; edge slots strided over the segment, fixed-order tree over
+// the slots.  A single-segment hub is finished here; otherwise the partial goes to ws[seg] for k_agg_combine.
 constexpr int kLongThreads = 1024;
-__global__ void __launch_bounds__(kLongThreads) k_agg_fwd_long(AggArgs a, const int32_t *__restrict__ long_rows) {
+__global__ void __launch_bounds__(kLongThreads) k_agg_fwd_long(AggArgs a, HubSegs h) {
   extern __shared__ float red[];  // [nslots][oc]
   const int od = a.odim;
-  const int i = long_rows[blockIdx.x];
+  const int sg = blockIdx.x;
+  const int hub = h.seg_hub[sg];
+  const int i = h.long_ids[hub];
+  const int first = h.seg_first[hub], nseg = h.seg_first[hub + 1] - first;
+  const int off = (sg - first) * h.seg;
   const int oc = min(od, kLongThreads);
   const int nslots = kLongThreads / oc;
   const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
   for (int o0 = 0; o0 < od; o0 += oc) {
     const int o = o0 + ol;
     float acc = 0.f;
-    if (slot < nslots && o < od) acc = agg_edges(a, i, o, slot, nslots);
+    if (slot < nslots && o < od) acc = agg_edges(a, i, o, slot, nslots, off, h.seg);
     if (slot < nslots) red[slot * oc + ol] = acc;
     __syncthreads();
     for (int s = 1; s < nslots; s <<= 1) {
       if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
       __syncthreads();
     }
-    if (slot == 0 && o < od) agg_store(a, i, o, red[ol]);
+    if (slot == 0 && o < od) {
+      if (nseg == 1) agg_store(a, i, o, red[ol]);
+      else h.ws[(size_t)sg * od + o] = red[ol];
+    }
     __syncthreads();
+  }
+}
+__global__ void k_agg_combine(AggArgs a, HubSegs h) {
+  const int hub = blockIdx.x;
+  const int first = h.seg_first[hub], nseg = h.seg_first[hub + 1] - first;
+  if (nseg <= 1) return;
+  const int i = h.long_ids[hub];
+  for (int o = threadIdx.x; o < a.odim; o += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < nseg; ++s) acc += h.ws[(size_t)(first + s) * a.odim + o];
+    agg_store(a, i, o, acc);
   }
 }
 
@@ -496,17 +523,23 @@ int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X,
   return 0;
 }
 
-int launch_agg(const AggArgs &g, const int32_t *long_rows, int n_long, cudaStream_t st, const char *prof_name) {
+int launch_agg(const AggArgs &g, const HubSegs &h, cudaStream_t st, const char *prof_name) {
   if (g.ND <= 0) return 0;
   const int rows_per_warp = g.odim >= 32 ? 1 : 32 / g.odim;
   unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
   mrgcn::prof_begin(prof_name, st);
   k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
   MRGCN_LAUNCH_CHECK();
-  if (n_long > 0) {
+  if (h.n_long > 0) {
+    MRGCN_REQUIRE(h.ws || h.n_segs == h.n_long, MRGCN_E_BADARG, "agg: hub_ws missing");
     mrgcn::prof_begin("agg_long", st);
-    k_agg_fwd_long<<<(unsigned)n_long, kLongThreads, kLongThreads * sizeof(float), st>>>(g, long_rows);
+    k_agg_fwd_long<<<(unsigned)h.n_segs, kLongThreads, kLongThreads * sizeof(float), st>>>(g, h);
     MRGCN_LAUNCH_CHECK();
+    if (h.n_segs > h.n_long) {
+      mrgcn::prof_begin("agg_combine", st);
+      k_agg_combine<<<(unsigned)h.n_long, 128, 0, st>>>(g, h);
+      MRGCN_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
@@ -555,6 +588,7 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
   }
   // long rows are those of either graph; the host side builds the union list on the owner graph
   g.thresh = gl->n_long_rows > 0 ? gl->long_row_thresh : 0;
-  if (int rc = launch_agg(g, gl->long_rows, gl->n_long_rows, st, "agg_fwd")) return rc;
+  HubSegs hs{gl->long_rows, gl->row_seg_hub, gl->row_seg_first, gl->n_long_rows, gl->n_row_segs, gl->long_seg, a->hub_ws};
+  if (int rc = launch_agg(g, hs, st, "agg_fwd")) return rc;
   return 0;
 }

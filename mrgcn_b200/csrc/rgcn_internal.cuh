@@ -25,8 +25,14 @@ int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int
 // msg[e3,:] = val_e * Xrows[gather[e3], :] . W[r]   (gather = e3_src forward, e3_dst for the input gradient)
 int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
                     int out, cudaStream_t st, const char *prof_name);
-// segmented sums of AggArgs over n_rows rows (+ hub rows listed in long_rows)
-int launch_agg(const AggArgs &a, const int32_t *long_rows, int n_long, cudaStream_t st, const char *prof_name);
+// segmented sums of AggArgs over a.ND rows; hub rows (long_rows) are processed one CTA per segment of `seg` edges
+// (seg_hub/seg_first describe the segments), partial sums in hub_ws, combined in segment order
+struct HubSegs {
+  const int32_t *long_ids, *seg_hub, *seg_first;
+  int n_long, n_segs, seg;
+  float *ws;
+};
+int launch_agg(const AggArgs &a, const HubSegs &h, cudaStream_t st, const char *prof_name);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
 struct IdentPipe;

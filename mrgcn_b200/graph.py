@@ -18,7 +18,8 @@ import torch
 
 from . import _native as nv
 
-LONG_THRESH = 128      # rows / sources with more edges than this get a CTA of their own
+LONG_THRESH = 128      # rows / sources with more edges than this ("hubs") are handled by CTAs of their own
+LONG_SEG = 512         # ... one CTA per segment of this many edges; partial sums combined in segment order
 _I32 = torch.int32
 
 
@@ -62,6 +63,16 @@ class RelGraph:
         deg_c = self.colptr[1:] - self.colptr[:-1]
         self.long_rows = torch.nonzero(deg_r > LONG_THRESH).flatten().to(_I32)
         self.long_cols = torch.nonzero(deg_c > LONG_THRESH).flatten().to(_I32)
+        def segments(deg, hubs):
+            d = deg[hubs.long()].cpu().numpy().astype(np.int64)
+            nseg = (d + LONG_SEG - 1) // LONG_SEG
+            first = np.zeros(len(d) + 1, dtype=np.int64)
+            np.cumsum(nseg, out=first[1:])
+            hub = np.repeat(np.arange(len(d)), nseg)
+            mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+            return mk(hub if len(hub) else [0]), mk(first), int(first[-1])
+        self.row_seg_hub, self.row_seg_first, self.n_row_segs = segments(deg_r, self.long_rows)
+        self.col_seg_hub, self.col_seg_first, self.n_col_segs = segments(deg_c, self.long_cols)
         relptr = self.relptr.cpu().numpy().astype(np.int64)
         ch = chunk or _chunk_size(self.E)
         cnt = np.diff(relptr)
@@ -89,6 +100,9 @@ class RelGraph:
         c.n_long_rows, c.long_row_thresh = len(self.long_rows), LONG_THRESH
         c.long_cols = self.long_cols.data_ptr() if len(self.long_cols) else None
         c.n_long_cols, c.long_col_thresh = len(self.long_cols), LONG_THRESH
+        c.row_seg_hub, c.row_seg_first = self.row_seg_hub.data_ptr(), self.row_seg_first.data_ptr()
+        c.col_seg_hub, c.col_seg_first = self.col_seg_hub.data_ptr(), self.col_seg_first.data_ptr()
+        c.n_row_segs, c.n_col_segs, c.long_seg = self.n_row_segs, self.n_col_segs, LONG_SEG
         c.chunk_rel, c.chunk_ptr = self.chunk_rel.data_ptr(), self.chunk_ptr.data_ptr()
         c.rel_chunk_ptr, c.n_chunks = self.rel_chunk_ptr.data_ptr(), n_chunks
 

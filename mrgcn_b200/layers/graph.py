@@ -17,6 +17,12 @@ def _empty(n, like_dev):
     return torch.empty(max(int(n), 1), dtype=torch.float32, device=like_dev)
 
 
+def _hub_ws(gI, gF, in_dim, out_dim, B, dev):
+    """Workspace for the partial sums of hub segments (include/mrgcn_b200.h: hub_ws)."""
+    segs = max([max(g.n_row_segs, g.n_col_segs) for g in (gI, gF) if g is not None] + [0])
+    return _empty(segs * max(out_dim, in_dim, max(B, 1) * out_dim), dev) if segs else None
+
+
 class _LayerFn(torch.autograd.Function):
     """out = act(mask * (b + A.W_I(mixed) + A.(X W_F(mixed))))  — graph.py:62-102 + rgcn.py:78-87."""
 
@@ -53,6 +59,8 @@ class _LayerFn(torch.autograd.Function):
         for k, t in tens.items():
             setattr(a, k, nv.ptr(t))
         a.wmix, a.msg_I, a.msg_F, a.out = nv.ptr(wmix), nv.ptr(msg_I), nv.ptr(msg_F), nv.ptr(out)
+        hub_ws = _hub_ws(gI if hasI else None, gF if hasF else None, in_dim, out_dim, B, dev)
+        a.hub_ws = nv.ptr(hub_ws)
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_fwd(C.byref(a), nv.stream_ptr()), "rgcn_layer_fwd")
         ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims = gI, gF, B, bool(relu), (in_dim, out_dim)
@@ -110,6 +118,8 @@ class _LayerFn(torch.autograd.Function):
         b.g_bias, b.g_X = nv.ptr(g_b), nv.ptr(g_X)
         b.gact, b.cbuf, b.part, b.g_wmix, b.colsum_ws = nv.ptr(gact), nv.ptr(cbuf), nv.ptr(part), nv.ptr(g_wmix), nv.ptr(colsum)
         b.wt_ws, b.msgx_ws = nv.ptr(wt_ws), nv.ptr(msgx_ws)
+        hub_ws = _hub_ws(gI if hasI else None, gF if hasF else None, in_dim, out_dim, B, dev)
+        f.hub_ws = nv.ptr(hub_ws)
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
         g_add = gact[:g0.ND * out_dim].view(g0.ND, out_dim) if (ctx.has_addend and need[11]) else None

@@ -29,14 +29,18 @@ from .graph import RelGraph
 from .layers.graph import GraphConvolution, _LayerFn
 
 
-def balanced_bounds(weight, parts):
+def balanced_bounds(weight, parts, align=4):
     """Contiguous ranges [b[p], b[p+1]) over len(weight) nodes whose weight sums are as equal as a prefix
-    cut allows.  weight: 1-D array of non-negative per-node costs (stored entries touching the node)."""
+    cut allows.  weight: 1-D array of non-negative per-node costs (stored entries touching the node).
+    Interior cuts are rounded to multiples of `align` nodes so that a shard's rows of weight_I start 16-byte
+    aligned (the TMA-engine kernels need that)."""
     w = np.asarray(weight, dtype=np.float64)
     n = len(w)
     c = np.concatenate([[0.0], np.cumsum(w + 1e-9)])
     targets = c[-1] * np.arange(1, parts) / parts
     cuts = np.searchsorted(c, targets, side="left")
+    if align > 1 and n >= parts * align:
+        cuts = (cuts + align // 2) // align * align
     b = np.concatenate([[0], np.clip(cuts, 0, n), [n]]).astype(np.int64)
     return np.maximum.accumulate(b)
 

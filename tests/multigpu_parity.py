@@ -1,0 +1,47 @@
+# 2-rank correctness of the partitioned model against the single-GPU model (same weights), then timing
+import os, sys, torch, numpy as np, torch.distributed as dist, torch.nn as nn
+sys.path.insert(0, os.getcwd())
+from mrgcn_b200.graph import RelGraph
+from mrgcn_b200.models.rgcn import RGCN
+from mrgcn_b200.partition import PartitionedRGCN, balanced_bounds, node_weights
+from mrgcn_b200.synth import synth_triples
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok = True
+for (N, P, T, dims, B, fl) in [(5000, 6, 40000, (24, 10, 11), 5, False), (4000, 5, 30000, (0, 16, 4), 0, True), (3000, 4, 20000, (0, 8), 3, True)]:
+    R = 2 * P + 1
+    tr = synth_triples(N, P, T, seed=3)
+    full = RelGraph.from_triples(tr, N, P, device=dev)
+    row, col, val = full.coo
+    modules = [(dims[k], dims[k + 1], "mrgcn", nn.ReLU() if k + 2 < len(dims) else None) for k in range(len(dims) - 1)]
+    torch.manual_seed(0)
+    ref = RGCN(modules, R, N, B if B else -1, 0.0, fl, True, False)
+    X = torch.randn(N, dims[0]) if not fl else None
+    G = torch.randn(N, dims[-1])
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+    ref.to(dev)
+    out_ref = ref(X.to(dev) if X is not None else None, full)
+    (out_ref * G.to(dev)).sum().backward()
+    bounds = balanced_bounds(node_weights(row, col, N), world)
+    m = PartitionedRGCN(modules, R, N, B if B else -1, fl, True, False, bounds, rank)
+    m.load_full_state(state); m.to(dev); m.set_graph(row, col, val)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    out = m(X.to(dev) if X is not None else None)
+    (out * G[lo:hi].to(dev)).sum().backward(); m.sync_grads()
+    def chk(a, b, what):
+        global ok
+        err = float((a - b).abs().max()); tol = 1e-6 + 1e-5 * float(b.abs().max())
+        if err > tol: ok = False; print("rank", rank, "MISMATCH", what, err, tol)
+    chk(out, out_ref[lo:hi], "out")
+    refp = dict(ref.named_parameters())
+    for n, p in m.named_parameters():
+        want = refp[n].grad
+        if n == "layers.layer_0.weight_I":
+            S = want.shape[0] // N
+            want = want.view(S, N, -1)[:, lo:hi, :].reshape(S * (hi - lo), -1)
+        chk(p.grad, want, n)
+    if rank == 0: print("case", N, dims, B, "done; ok so far:", ok, "bounds", bounds.tolist())
+t = torch.tensor([1.0 if ok else 0.0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0: print("MULTIGPU PARITY", "PASS" if t.item() == 1.0 else "FAIL")
+dist.destroy_process_group()
