@@ -45,6 +45,9 @@ int64_t mrgcn_launch_count(void);
  * by CUDA events on its own stream.  mrgcn_profile_dump synchronises the device, writes one line per kernel
  * name ("name launches total_ms\n") into buf (NUL terminated, truncated to cap) and clears the records;
  * returns the number of bytes the full text needs. */
+/* Tensor-core (tcgen05, 3xTF32 split) variant of the feature-term message kernel: 0 = never, 1 = whenever it
+ * applies (out <= 32), 2 = only where it pays (16 < out <= 32; default, also MRGCN_FEAT_TC in the environment). */
+void mrgcn_set_feat_tc(int mode);
 void mrgcn_profile_enable(int on);
 int64_t mrgcn_profile_dump(char *buf, int64_t cap);
 

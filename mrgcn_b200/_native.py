@@ -65,6 +65,7 @@ SYMBOLS = {
     "mrgcn_version": (C.c_int, []),
     "mrgcn_last_error_string": (C.c_char_p, []),
     "mrgcn_launch_count": (C.c_int64, []),
+    "mrgcn_set_feat_tc": (None, [C.c_int]),
     "mrgcn_profile_enable": (None, [C.c_int]),
     "mrgcn_profile_dump": (C.c_int64, [C.c_char_p, C.c_int64]),
     "mrgcn_graph_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,

@@ -63,4 +63,9 @@ __device__ __forceinline__ int ldg_stream(const int *p) {
   return v;
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): two independent round-to-nearest FMAs per instruction -> half the issue slots
+// of the scalar form, bit-identical results.  acc.{x,y} += s * w.{x,y}
+__device__ __forceinline__ void fma2(float2 &acc, float s, float2 w) { acc = __ffma2_rn(make_float2(s, s), w, acc); }
+__device__ __forceinline__ void fma2v(float2 &acc, float2 a, float2 b) { acc = __ffma2_rn(a, b, acc); }
+
 }  // namespace mrgcn

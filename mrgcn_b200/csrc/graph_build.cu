@@ -29,29 +29,29 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- per-kernel profile: events bracket each launch on its own stream; read back after a sync --------
-struct ProfRec { const char *name; cudaEvent_t a, b; };
+struct ProfRec { std::string name; cudaEvent_t a, b; bool open; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
-static thread_local ProfRec g_pending = {nullptr, nullptr, nullptr};
+static thread_local ProfRec g_pending = {std::string(), nullptr, nullptr, false};
 static thread_local cudaStream_t g_pending_stream = nullptr;
 
 void prof_begin(const char *name, cudaStream_t st) {
   if (!g_prof_on) return;
-  ProfRec r{name, nullptr, nullptr};
+  ProfRec r{std::string(name), nullptr, nullptr, true};
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, st);
   g_pending = r;
   g_pending_stream = st;
 }
 void prof_end() {
-  if (!g_pending.name) return;
+  if (!g_pending.open) return;
   cudaEventRecord(g_pending.b, g_pending_stream);
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(g_pending);
   }
-  g_pending.name = nullptr;
+  g_pending.open = false;
 }
 
 namespace {

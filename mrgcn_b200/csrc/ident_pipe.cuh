@@ -50,7 +50,7 @@ __device__ __forceinline__ void ident_pipeline(const IdentPipe &p, const float *
         const int a_lo = e_lo & ~3;
         int cnt = min(e_hi - a_lo, p.mcap);
         cnt = e_hi > e_lo ? ((cnt + 3) & ~3) : 0;
-        mbar_wait(&empty[s], ((k / S) & 1) ^ 1);          // stage drained by every consumer warp
+        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, 7);  // stage drained by every consumer warp
         unsigned char *st = stage_base + (size_t)s * p.stage_bytes;
         int *hdr = reinterpret_cast<int *>(st);
         hdr[0] = e_lo; hdr[1] = e_hi; hdr[2] = j0; hdr[3] = a_lo;

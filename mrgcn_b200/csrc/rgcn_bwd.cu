@@ -135,18 +135,20 @@ __device__ __forceinline__ void ident_bwd_c_edge(const float *__restrict__ vrow,
       const float *row = vp + (size_t)b * bstride;
       float acc = 0.f;
       if constexpr (VW == 4) {
+        float2 a2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < OC / 4; ++q) {
           float4 w = reinterpret_cast<const float4 *>(row)[q];
-          acc = fmaf(w.x, t[4 * q + 0], acc); acc = fmaf(w.y, t[4 * q + 1], acc);
-          acc = fmaf(w.z, t[4 * q + 2], acc); acc = fmaf(w.w, t[4 * q + 3], acc);
+          fma2v(a2, make_float2(w.x, w.y), make_float2(t[4 * q + 0], t[4 * q + 1]));
+          fma2v(a2, make_float2(w.z, w.w), make_float2(t[4 * q + 2], t[4 * q + 3]));
         }
+        acc = a2.x + a2.y;
       } else if constexpr (VW == 2) {
+        float2 a2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < OC / 2; ++q) {
-          float2 w = reinterpret_cast<const float2 *>(row)[q];
-          acc = fmaf(w.x, t[2 * q + 0], acc); acc = fmaf(w.y, t[2 * q + 1], acc);
-        }
+        for (int q = 0; q < OC / 2; ++q)
+          fma2v(a2, reinterpret_cast<const float2 *>(row)[q], make_float2(t[2 * q + 0], t[2 * q + 1]));
+        acc = a2.x + a2.y;
       } else {
 #pragma unroll
         for (int q = 0; q < OC; ++q)
@@ -273,9 +275,9 @@ k_ident_bwd_w(const float *__restrict__ comp, const int32_t *__restrict__ colptr
       s_hi = colptr[j0 + jl + 1];
       if (thresh > 0 && s_hi - s_lo > thresh) s_hi = s_lo;  // hub: other kernel
     }
-    float acc[BT];
+    float2 acc[BT / 2];
 #pragma unroll
-    for (int q = 0; q < BT; ++q) acc[q] = 0.f;
+    for (int q = 0; q < BT / 2; ++q) acc[q] = make_float2(0.f, 0.f);
     for (int c_lo = t_lo; c_lo < t_hi; c_lo += EC) {
       const int c_hi = min(t_hi, c_lo + EC);
       __syncthreads();
@@ -294,17 +296,17 @@ k_ident_bwd_w(const float *__restrict__ comp, const int32_t *__restrict__ colptr
 #pragma unroll
         for (int q = 0; q < BT / 4; ++q) {
           float4 c = c4[q];
-          acc[4 * q + 0] = fmaf(c.x, t, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(c.y, t, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(c.z, t, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(c.w, t, acc[4 * q + 3]);
+          fma2(acc[2 * q], t, make_float2(c.x, c.y));
+          fma2(acc[2 * q + 1], t, make_float2(c.z, c.w));
         }
       }
     }
     if (mine && !(thresh > 0 && colptr[j0 + jl + 1] - colptr[j0 + jl] > thresh)) {
 #pragma unroll
-      for (int q = 0; q < BT; ++q)
-        if (q < B) gW[((size_t)q * NS + j0) * out + tid] = acc[q];
+      for (int q = 0; q < BT / 2; ++q) {
+        if (2 * q < B) gW[((size_t)(2 * q) * NS + j0) * out + tid] = acc[q].x;
+        if (2 * q + 1 < B) gW[((size_t)(2 * q + 1) * NS + j0) * out + tid] = acc[q].y;
+      }
     }
   }
 }
@@ -460,9 +462,9 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
   const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
   const bool kin = k < in;
   for (int c0 = 0; c0 < out; c0 += OC) {
-    float acc[OC];
+    float2 acc[OC / 2];
 #pragma unroll
-    for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+    for (int o = 0; o < OC / 2; ++o) acc[o] = make_float2(0.f, 0.f);
     for (int eb = e_lo; eb < e_hi; eb += EB) {
       const int nb = min(EB, e_hi - eb);
       __syncthreads();
@@ -482,10 +484,8 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
 #pragma unroll
           for (int q = 0; q < OC / 4; ++q) {
             float4 t = t4[q];
-            acc[4 * q + 0] = fmaf(x, t.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(x, t.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(x, t.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(x, t.w, acc[4 * q + 3]);
+            fma2(acc[2 * q], x, make_float2(t.x, t.y));
+            fma2(acc[2 * q + 1], x, make_float2(t.z, t.w));
           }
         }
       }
@@ -493,8 +493,10 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
     if (kin) {
       float *pp = part + ((size_t)c * in + k) * out + c0;
 #pragma unroll
-      for (int o = 0; o < OC; ++o)
-        if (c0 + o < out) pp[o] = acc[o];
+      for (int o = 0; o < OC / 2; ++o) {
+        if (c0 + 2 * o < out) pp[2 * o] = acc[o].x;
+        if (c0 + 2 * o + 1 < out) pp[2 * o + 1] = acc[o].y;
+      }
     }
   }
 }

@@ -44,6 +44,9 @@ __global__ void k_basis_mix_fwd(const float *__restrict__ comp, const float *__r
 template <int OC, int VW>
 __device__ __forceinline__ void mix_bases(const float *__restrict__ vp, size_t bstride, const float *__restrict__ cr,
                                           int B, float (&acc)[OC]) {
+  float2 a2[OC / 2];
+#pragma unroll
+  for (int q = 0; q < OC / 2; ++q) a2[q] = make_float2(acc[2 * q], acc[2 * q + 1]);
 #pragma unroll 4
   for (int b = 0; b < B; ++b) {
     const float c = cr[b];
@@ -52,23 +55,19 @@ __device__ __forceinline__ void mix_bases(const float *__restrict__ vp, size_t b
 #pragma unroll
       for (int q = 0; q < OC / 4; ++q) {
         float4 t = reinterpret_cast<const float4 *>(row)[q];
-        acc[4 * q + 0] = fmaf(c, t.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(c, t.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(c, t.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(c, t.w, acc[4 * q + 3]);
+        fma2(a2[2 * q], c, make_float2(t.x, t.y));
+        fma2(a2[2 * q + 1], c, make_float2(t.z, t.w));
       }
     } else if constexpr (VW == 2) {
 #pragma unroll
-      for (int q = 0; q < OC / 2; ++q) {
-        float2 t = reinterpret_cast<const float2 *>(row)[q];
-        acc[2 * q + 0] = fmaf(c, t.x, acc[2 * q + 0]);
-        acc[2 * q + 1] = fmaf(c, t.y, acc[2 * q + 1]);
-      }
+      for (int q = 0; q < OC / 2; ++q) fma2(a2[q], c, reinterpret_cast<const float2 *>(row)[q]);
     } else {
 #pragma unroll
-      for (int q = 0; q < OC; ++q) acc[q] = fmaf(c, row[q], acc[q]);
+      for (int q = 0; q < OC / 2; ++q) fma2(a2[q], c, make_float2(row[2 * q], row[2 * q + 1]));
     }
   }
+#pragma unroll
+  for (int q = 0; q < OC / 2; ++q) { acc[2 * q] = a2[q].x; acc[2 * q + 1] = a2[q].y; }
 }
 
 // per-edge work of one staged tile: RS = row stride (floats) of a (basis, source) row in the tile
@@ -223,9 +222,9 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
         }
         cp_async_commit();
       };
-      float acc[OC];
+      float2 acc[OC / 2];
 #pragma unroll
-      for (int o = 0; o < OC; ++o) acc[o] = 0.f;
+      for (int o = 0; o < OC / 2; ++o) acc[o] = make_float2(0.f, 0.f);
       __syncwarp();
       prefetch(0, 0);
       for (int kc = 0; kc < nkc; ++kc) {
@@ -245,10 +244,8 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
 #pragma unroll
           for (int q = 0; q < OC / 4; ++q) {
             float4 t = w4[q];
-            acc[4 * q + 0] = fmaf(x, t.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(x, t.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(x, t.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(x, t.w, acc[4 * q + 3]);
+            fma2(acc[2 * q], x, make_float2(t.x, t.y));
+            fma2(acc[2 * q + 1], x, make_float2(t.z, t.w));
           }
         }
         __syncwarp();  // all lanes done with buffer (kc & 1) before it is refilled two chunks later
@@ -257,8 +254,10 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
         const float v = e3_val[e];
         float *mp = msg + (size_t)e * out + c0;
 #pragma unroll
-        for (int o = 0; o < OC; ++o)
-          if (c0 + o < out) mp[o] = v * acc[o];
+        for (int o = 0; o < OC / 2; ++o) {
+          if (c0 + 2 * o < out) mp[2 * o] = v * acc[o].x;
+          if (c0 + 2 * o + 1 < out) mp[2 * o + 1] = v * acc[o].y;
+        }
       }
     }
   }
@@ -501,6 +500,11 @@ static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const floa
 int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
                     int out, cudaStream_t st, const char *prof_name) {
   if (g->n_chunks == 0) return 0;
+  {
+    int launched = 0;
+    if (int rc = launch_feat_msg_tc(g, gather, X, W, msg, in, out, st, prof_name, &launched)) return rc;
+    if (launched) return 0;
+  }
   const int OC = pick_oc(out);
   const int INP = (int)cdiv(in, KC) * KC;
   size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 2 * 32 * (KC + 1)) * 4;

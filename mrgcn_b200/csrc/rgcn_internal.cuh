@@ -33,6 +33,9 @@ struct HubSegs {
   float *ws;
 };
 int launch_agg(const AggArgs &a, const HubSegs &h, cudaStream_t st, const char *prof_name);
+// tensor-core (tcgen05, 3xTF32) variant of launch_feat_msg; *launched = 0 when it does not apply
+int launch_feat_msg_tc(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
+                       int out, cudaStream_t st, const char *prof_name, int *launched);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
 struct IdentPipe;

@@ -357,3 +357,42 @@ def test_ranks_vs_oracle():
         ref = rp.compute_ranks(data, E, Rel, 50, filtered).numpy()
         got = lp.compute_ranks_fast(data, E.to(DEV), Rel.to(DEV), 50, filtered).cpu().numpy()
         assert np.array_equal(ref, got)     # integer-valued scores: sums are exact in fp32, so ranks are too
+
+
+@pytest.mark.parametrize("indim,outdim", [(151, 10), (40, 24), (9, 6)])
+def test_feature_term_tensor_core_path(indim, outdim):
+    """The tcgen05 (split-TF32) variant of the feature-term kernel against the CUDA-core variant and the oracle."""
+    from mrgcn_b200 import _native as nv
+    from mrgcn_b200.graph import RelGraph
+    from mrgcn_b200.layers.graph import GraphConvolution
+    from mrgcn_b200.synth import synth_triples
+    from oracle import reference_port as rp
+    N, P, B = 2500, 5, 3
+    R = 2 * P + 1
+    A = rp.csr_to_coo(rp.as_float32(rp.stacked_adjacency(synth_triples(N, P, 20000, seed=9), N, P)), torch.float32)
+    torch.manual_seed(5)
+    layer = GraphConvolution(indim, outdim, R, N, num_bases=B, bias=True, input_layer=False)
+    params = {k: v.detach().clone() for k, v in layer.named_parameters()}
+    X = torch.randn(N, indim)
+    ref = rp.graphconv_forward(params, X, A, num_nodes=N, num_relations=R, num_bases=B, input_layer=False, featureless=False)
+    layer.to(DEV)
+    rg = RelGraph.from_coo(A, R)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            nv.lib().mrgcn_set_feat_tc(mode)
+            nv.profile_dump()
+            nv.profile_enable(True)
+            Xg = X.to(DEV).requires_grad_(True)
+            out = layer(Xg, rg)
+            out.sum().backward()
+            names = set(nv.profile_dump())
+            nv.profile_enable(False)
+            assert ("feat_msg_fwd_tc" in names) == (mode == 1)
+            outs[mode] = (out.detach().cpu(), Xg.grad.cpu())
+    finally:
+        nv.lib().mrgcn_set_feat_tc(-1)
+        nv.profile_enable(False)
+    scaled_close(outs[1][0], ref, "tensor-core out vs oracle")
+    scaled_close(outs[1][0], outs[0][0], "tensor-core out vs CUDA-core out")
+    scaled_close(outs[1][1], outs[0][1], "tensor-core dX vs CUDA-core dX")
