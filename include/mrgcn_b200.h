@@ -20,7 +20,9 @@
  * column c = r*NS + j; mrgcn/encodings/graph_structure.py:33-38):
  *   E1  destination-major  sorted by (dst, rel, src)   rowptr[ND+1]
  *   E2  source-major       sorted by (src, rel, dst)   colptr[NS+1]
- *   E3  relation-major     sorted by (rel, src, dst)   relptr[R+1]
+ *   E3  relation-major     sorted by (source slab, rel, src, dst)   relptr[n_slabs*R+1]
+ *       A slab is `slab_rows` consecutive sources: the relation-major kernels gather feature rows of one slab at a
+ *       time, so that the slab (tens of MB) stays L2-resident and every row is fetched from HBM once, not once per edge.
  */
 #ifndef MRGCN_B200_H
 #define MRGCN_B200_H
@@ -70,7 +72,7 @@ typedef struct mrgcn_graph {
   float   *e2_val;   /* [E] */
   int32_t *e2_to_e3; /* [E] position of the same edge in E3 */
   /* E3 */
-  int32_t *relptr;   /* [R+1] */
+  int32_t *relptr;   /* [n_slabs*R+1] edge range of group g = slab*R + rel */
   int32_t *e3_src;   /* [E] */
   int32_t *e3_dst;   /* [E] */
   float   *e3_val;   /* [E] */
@@ -86,8 +88,9 @@ typedef struct mrgcn_graph {
   int32_t n_row_segs, n_col_segs, long_seg, _pad3;
   int32_t *chunk_rel;  /* [n_chunks] relation of E3 chunk c */
   int32_t *chunk_ptr;  /* [n_chunks+1] E3 edge range of chunk c (never crosses a relation) */
-  int32_t *rel_chunk_ptr; /* [R+1] chunk range of relation r */
-  int32_t n_chunks, _pad2;
+  int32_t *rel_chunk_ptr; /* [R+1] range in rel_chunk_idx of relation r */
+  int32_t *rel_chunk_idx; /* [n_chunks] chunk ids of each relation, in slab order */
+  int32_t n_chunks, slab_rows; /* slab_rows: input of mrgcn_graph_build (0 = one slab) */
 } mrgcn_graph;
 
 /* Re-emit the reference's stacked adjacency as E1/E2/E3.

@@ -33,7 +33,7 @@ class Graph(C.Structure):
         ("col_seg_first", C.c_void_p), ("n_row_segs", C.c_int32), ("n_col_segs", C.c_int32), ("long_seg", C.c_int32),
         ("_pad3", C.c_int32),
         ("chunk_rel", C.c_void_p), ("chunk_ptr", C.c_void_p), ("rel_chunk_ptr", C.c_void_p),
-        ("n_chunks", C.c_int32), ("_pad2", C.c_int32),
+        ("rel_chunk_idx", C.c_void_p), ("n_chunks", C.c_int32), ("slab_rows", C.c_int32),
     ]
 
 

@@ -112,7 +112,8 @@ __global__ void k_fill_e2(const int32_t *__restrict__ e2_to_e1, const int32_t *_
                           const float *__restrict__ e1_val, int32_t *__restrict__ e2_src,
                           int32_t *__restrict__ e2_dst, int32_t *__restrict__ e2_rel,
                           float *__restrict__ e2_val, int32_t *__restrict__ e1_to_e2,
-                          uint32_t *__restrict__ key3, int32_t *__restrict__ ident, int64_t E) {
+                          uint32_t *__restrict__ key3, int32_t *__restrict__ ident, int64_t E, int32_t slab_rows,
+                          int32_t R) {
   int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (q >= E) return;
   int32_t p = e2_to_e1[q];
@@ -122,7 +123,7 @@ __global__ void k_fill_e2(const int32_t *__restrict__ e2_to_e1, const int32_t *_
   e2_rel[q] = r;
   e2_val[q] = e1_val[p];
   e1_to_e2[p] = (int32_t)q;
-  key3[q] = (uint32_t)r;
+  key3[q] = (uint32_t)(e1_src[p] / slab_rows) * (uint32_t)R + (uint32_t)r;   // E3 group = (source slab, relation)
   ident[q] = (int32_t)q;
 }
 
@@ -132,13 +133,13 @@ __global__ void k_fill_e3(const int32_t *__restrict__ e3_to_e2_in, const int32_t
                           int32_t *__restrict__ e3_src, int32_t *__restrict__ e3_dst,
                           int32_t *__restrict__ e3_rel, float *__restrict__ e3_val,
                           int32_t *__restrict__ e3_to_e2, int32_t *__restrict__ e1_to_e3, int32_t *__restrict__ e2_to_e3,
-                          int64_t E) {
+                          int64_t E, int32_t slab_rows, int32_t R) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= E) return;
   int32_t q = e3_to_e2_in[t];
   e3_src[t] = e2_src[q];
   e3_dst[t] = e2_dst[q];
-  e3_rel[t] = e2_rel[q];
+  e3_rel[t] = (e2_src[q] / slab_rows) * R + e2_rel[q];   // group id (slab, rel): non-decreasing in E3 order
   e3_val[t] = e2_val[q];
   e3_to_e2[t] = q;
   e2_to_e3[q] = (int32_t)t;
@@ -274,6 +275,10 @@ extern "C" int mrgcn_graph_build(const int64_t *coo_row, const int64_t *coo_col,
   MRGCN_REQUIRE((double)nrows * (double)ncols < 9.0e18, MRGCN_E_OVERFLOW, "graph_build: nrows*ncols exceeds 63 bits");
   int32_t NS = (int32_t)(ncols / R), ND = (int32_t)nrows;
   g->E = E; g->ND = ND; g->NS = NS; g->R = R;
+  const int32_t slab_rows = g->slab_rows > 0 ? g->slab_rows : (NS > 0 ? NS : 1);
+  const int64_t n_slabs = cdiv(NS > 0 ? NS : 1, slab_rows);
+  const int64_t n_groups = n_slabs * R;
+  MRGCN_REQUIRE(n_groups < (1ll << 31), MRGCN_E_OVERFLOW, "graph_build: too many (slab, relation) groups");
   const int T = 256;
   unsigned gridE = (unsigned)cdiv(E > 0 ? E : 1, T);
 
@@ -295,20 +300,20 @@ extern "C" int mrgcn_graph_build(const int64_t *coo_row, const int64_t *coo_col,
     int b2 = bits_for((uint64_t)NS * (uint64_t)R);
     if (int rc = sort_pairs(kA.as<uint64_t>(), kB.as<uint64_t>(), vA.as<int32_t>(), e2to1.as<int32_t>(), E, b2, st)) return rc;
     k_fill_e2<<<gridE, T, 0, st>>>(e2to1.as<int32_t>(), e1dst.as<int32_t>(), g->e1_src, g->e1_rel, g->e1_val, g->e2_src,
-                                   g->e2_dst, g->e2_rel, g->e2_val, g->e1_to_e2, kA.as<uint32_t>(), vA.as<int32_t>(), E);
+                                   g->e2_dst, g->e2_rel, g->e2_val, g->e1_to_e2, kA.as<uint32_t>(), vA.as<int32_t>(), E, slab_rows, R);
     MRGCN_LAUNCH_CHECK();
     // E3: stable sort of E2 by rel -> (rel, src, dst)
-    int b3 = bits_for((uint64_t)R);
+    int b3 = bits_for((uint64_t)n_groups);
     if (int rc = sort_pairs(kA.as<uint32_t>(), kB.as<uint32_t>(), vA.as<int32_t>(), vB.as<int32_t>(), E, b3, st)) return rc;
     k_fill_e3<<<gridE, T, 0, st>>>(vB.as<int32_t>(), e2to1.as<int32_t>(), g->e2_src, g->e2_dst, g->e2_rel, g->e2_val,
-                                   g->e3_src, g->e3_dst, e3rel.as<int32_t>(), g->e3_val, g->e3_to_e2, g->e1_to_e3, g->e2_to_e3, E);
+                                   g->e3_src, g->e3_dst, e3rel.as<int32_t>(), g->e3_val, g->e3_to_e2, g->e1_to_e3, g->e2_to_e3, E, slab_rows, R);
     MRGCN_LAUNCH_CHECK();
   }
   k_ptr<<<(unsigned)cdiv((int64_t)ND + 1, T), T, 0, st>>>(e1dst.as<int32_t>(), E, ND, g->rowptr);
   MRGCN_LAUNCH_CHECK();
   k_ptr<<<(unsigned)cdiv((int64_t)NS + 1, T), T, 0, st>>>(g->e2_src, E, NS, g->colptr);
   MRGCN_LAUNCH_CHECK();
-  k_ptr<<<(unsigned)cdiv((int64_t)R + 1, T), T, 0, st>>>(e3rel.as<int32_t>(), E, R, g->relptr);
+  k_ptr<<<(unsigned)cdiv((int64_t)n_groups + 1, T), T, 0, st>>>(e3rel.as<int32_t>(), E, (int32_t)n_groups, g->relptr);
   MRGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -10,6 +10,8 @@
 //                        B > 0: g_weight_F[b] = sum_r comp_F[r,b] g_W[r],  g_comp_F[r,b] = <weight_F[b], g_W[r]>
 //                        g_X[j,k] = sum_{e: src=j} sum_o t_e[o] * W[r_e,k,o]                   (E2, per source)
 // Every reduction is a segmented sum in a fixed order: bit-reproducible, no float atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pipeline.cuh"
 #include "ident_pipe.cuh"
@@ -66,11 +68,11 @@ k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const 
   }
 }
 
-// out[s, x] = sum_c part[c*width + x] for c in [seg_ptr[s], seg_ptr[s+1]) -- fixed order: 8 chunk slots stride the
+// out[s, x] = sum_c part[idx(c)*width + x] for c in [seg_ptr[s], seg_ptr[s+1]), idx = seg_idx[c] (or c) -- fixed order: 8 chunk slots stride the
 // segment (each slot sequential), then a fixed tree over the slots.  seg_ptr == NULL: one segment [0, nall).
 __global__ void __launch_bounds__(256)
-k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr, int nall, int width,
-             float *__restrict__ outp) {
+k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_idx,
+             int nall, int width, float *__restrict__ outp) {
   __shared__ float red[8][32];
   const int s = blockIdx.y;
   const int xl = threadIdx.x & 31, slot = threadIdx.x >> 5;
@@ -80,10 +82,10 @@ k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr
   if (x < width) {
     int c = lo + slot;
     for (; c + 8 < hi; c += 16) {
-      a0 += part[(size_t)c * width + x];
-      a1 += part[(size_t)(c + 8) * width + x];
+      a0 += part[(size_t)(seg_idx ? seg_idx[c] : c) * width + x];
+      a1 += part[(size_t)(seg_idx ? seg_idx[c + 8] : c + 8) * width + x];
     }
-    if (c < hi) a0 += part[(size_t)c * width + x];
+    if (c < hi) a0 += part[(size_t)(seg_idx ? seg_idx[c] : c) * width + x];
   }
   red[slot][xl] = a0 + a1;
   __syncthreads();
@@ -501,6 +503,101 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
   }
 }
 
+// Row-per-warp variant of the feature weight gradient (in <= 160, out <= 16): lane l owns rows k = c*32 + l of g_W for
+// every 32-wide chunk c (NK*OC accumulators in registers), reads each edge's feature row with NK coalesced 128-byte
+// loads and t_e from a per-warp shared-memory batch (broadcast).  4 warps split the chunk's edge batches; their partial
+// sums are added in warp order.  ~3x fewer shared-pipe wavefronts than k_feat_bwd_w (ncu r01_feat: that one is bound by
+// the L1/shared data pipe).
+template <int NK, int OC>
+__global__ void __launch_bounds__(128)
+k_feat_bwd_w_rw(const float *__restrict__ X, const float *__restrict__ gact, const int32_t *__restrict__ chunk_ptr,
+                const int32_t *__restrict__ e3_src, const int32_t *__restrict__ e3_dst,
+                const float *__restrict__ e3_val, float *__restrict__ part, int in, int out) {
+  constexpr int P = OC / 2, NW = 4;
+  __shared__ __align__(16) float Ts[NW][32][OC];
+  __shared__ int Js[NW][32];
+  __shared__ float red[NW - 1][NK * 32 * OC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x;
+  const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
+  float2 acc[NK][P];
+#pragma unroll
+  for (int q = 0; q < NK; ++q)
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[q][p] = make_float2(0.f, 0.f);
+  for (int eb = e_lo + warp * 32; eb < e_hi; eb += NW * 32) {
+    const int nb = min(32, e_hi - eb);
+    __syncwarp();
+    {
+      const int e = eb + lane;
+      const bool live = lane < nb;
+      const float v = live ? e3_val[e] : 0.f;
+      const float *gp = gact + (size_t)(live ? e3_dst[e] : 0) * out;
+      Js[warp][lane] = live ? e3_src[e] : 0;
+#pragma unroll
+      for (int o = 0; o < OC; ++o) Ts[warp][lane][o] = (live && o < out) ? v * gp[o] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {  // padded entries have t = 0 and read row 0 (valid memory)
+      const int j = Js[warp][i];
+      float x[NK];
+#pragma unroll
+      for (int q = 0; q < NK; ++q) {
+        const int k = q * 32 + lane;
+        x[q] = (k < in) ? __ldg(X + (size_t)j * in + k) : 0.f;
+      }
+      float2 t[P];
+      if constexpr (OC % 4 == 0) {
+#pragma unroll
+        for (int p = 0; p < P; p += 2) {
+          const float4 t4 = *reinterpret_cast<const float4 *>(&Ts[warp][i][2 * p]);
+          t[p] = make_float2(t4.x, t4.y);
+          t[p + 1] = make_float2(t4.z, t4.w);
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) t[p] = *reinterpret_cast<const float2 *>(&Ts[warp][i][2 * p]);
+      }
+#pragma unroll
+      for (int q = 0; q < NK; ++q)
+#pragma unroll
+        for (int p = 0; p < P; ++p) fma2(acc[q][p], x[q], t[p]);
+    }
+  }
+  // partial sums of warps 1..3 -> shared memory, warp 0 adds them in warp order and stores
+  if (warp > 0) {
+#pragma unroll
+    for (int q = 0; q < NK; ++q)
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        red[warp - 1][(q * 32 + lane) * OC + 2 * p] = acc[q][p].x;
+        red[warp - 1][(q * 32 + lane) * OC + 2 * p + 1] = acc[q][p].y;
+      }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+      const int k = q * 32 + lane;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        float a = acc[q][p].x, b = acc[q][p].y;
+#pragma unroll
+        for (int w2 = 0; w2 < NW - 1; ++w2) {
+          a += red[w2][(q * 32 + lane) * OC + 2 * p];
+          b += red[w2][(q * 32 + lane) * OC + 2 * p + 1];
+        }
+        if (k < in) {
+          float *pp = part + ((size_t)c * in + k) * out;
+          if (2 * p < out) pp[2 * p] = a;
+          if (2 * p + 1 < out) pp[2 * p + 1] = b;
+        }
+      }
+    }
+  }
+}
+
 // ---- basis gradients of the feature weights (graph.py:83-85 backwards).  Tiny. ---------------------
 __global__ void k_basis_mix_bwd_v(const float *__restrict__ comp, const float *__restrict__ gW, float *__restrict__ gV,
                                   int R, int B, int IO) {
@@ -565,7 +662,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   if (a->g_bias) {
     if (ND > 0) {
       MRGCN_PROF("bias_reduce");
-  k_seq_reduce<<<dim3((unsigned)cdiv(out, 32), 1), 256, 0, st>>>(a->colsum_ws, nullptr, nblk, out, a->g_bias);
+  k_seq_reduce<<<dim3((unsigned)cdiv(out, 32), 1), 256, 0, st>>>(a->colsum_ws, nullptr, nullptr, nblk, out, a->g_bias);
       MRGCN_LAUNCH_CHECK();
     } else {
       MRGCN_CUDA(cudaMemsetAsync(a->g_bias, 0, sizeof(float) * out, st));
@@ -702,7 +799,8 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         }
         MRGCN_PROF("comp_reduce");
         k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)gI->R), 256, 0, st>>>(a->part, gI->rel_chunk_ptr,
-                                                                                    gI->n_chunks, B, a->g_comp_I);
+                                                                                    gI->rel_chunk_idx, gI->n_chunks, B,
+                                                                                    a->g_comp_I);
         MRGCN_LAUNCH_CHECK();
       }
     }
@@ -715,7 +813,33 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
     if (a->g_weight_F || a->g_comp_F) {
       float *gW = B > 0 ? a->g_wmix : a->g_weight_F;
       MRGCN_REQUIRE(gW && a->part, MRGCN_E_BADARG, "layer_bwd: g_wmix/part missing");
-      if (gF->E > 0) {
+      static int rw_mode = -1;
+      if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = !e ? 2 : (e[0] == '0' ? 0 : 1); }
+      if (gF->E > 0 && in <= 160 && out <= 16 && (rw_mode == 1 || (rw_mode == 2 && in > 64))) {
+        const int NK = (int)cdiv(in, 32);
+        const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
+        MRGCN_PROF("feat_bwd_w");
+#define LAUNCH_RW(NKV, OCV) \
+  k_feat_bwd_w_rw<NKV, OCV><<<(unsigned)gF->n_chunks, 128, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out)
+#define LAUNCH_NK(OCV)                  \
+  switch (NK) {                         \
+    case 1: LAUNCH_RW(1, OCV); break;   \
+    case 2: LAUNCH_RW(2, OCV); break;   \
+    case 3: LAUNCH_RW(3, OCV); break;   \
+    case 4: LAUNCH_RW(4, OCV); break;   \
+    default: LAUNCH_RW(5, OCV); break;  \
+  }
+        switch (OCR) {
+          case 4: LAUNCH_NK(4); break;
+          case 8: LAUNCH_NK(8); break;
+          case 10: LAUNCH_NK(10); break;
+          case 12: LAUNCH_NK(12); break;
+          default: LAUNCH_NK(16); break;
+        }
+#undef LAUNCH_NK
+#undef LAUNCH_RW
+        MRGCN_LAUNCH_CHECK();
+      } else if (gF->E > 0) {
         const int OC = pick_oc(out);
         int bt = (int)cdiv(in < 256 ? in : 256, 32) * 32;
         dim3 grid((unsigned)gF->n_chunks, (unsigned)cdiv(in, bt));
@@ -730,7 +854,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       }
       MRGCN_PROF("feat_w_reduce");
   k_seq_reduce<<<dim3((unsigned)cdiv(IO, 32), (unsigned)gF->R), 256, 0, st>>>(a->part, gF->rel_chunk_ptr,
-                                                                                   gF->n_chunks, IO, gW);
+                                                                                   gF->rel_chunk_idx, gF->n_chunks, IO, gW);
       MRGCN_LAUNCH_CHECK();
       if (B > 0) {
         if (a->g_weight_F) {

@@ -19,6 +19,7 @@ import torch
 from . import _native as nv
 
 LONG_THRESH = 128      # rows / sources with more edges than this ("hubs") are handled by CTAs of their own
+SLAB_ROWS = 32768      # sources per slab of the relation-major order (a slab of feature rows stays L2-resident)
 LONG_SEG = 512         # ... one CTA per segment of this many edges; partial sums combined in segment order
 _I32 = torch.int32
 
@@ -37,14 +38,16 @@ class RelGraph:
         e = self.E + 8          # slack: the TMA-engine kernels copy edge ranges rounded up to 16 bytes
         mk_i = lambda n: torch.empty(n, dtype=_I32, device=device)
         mk_f = lambda n: torch.empty(n, dtype=torch.float32, device=device)
-        self.rowptr, self.colptr, self.relptr = mk_i(ND + 1), mk_i(NS + 1), mk_i(R + 1)
+        self.slab_rows = SLAB_ROWS
+        self.n_slabs = max(1, -(-NS // self.slab_rows))
+        self.rowptr, self.colptr, self.relptr = mk_i(ND + 1), mk_i(NS + 1), mk_i(self.n_slabs * R + 1)
         self.e1_src, self.e1_rel, self.e1_val = mk_i(e), mk_i(e), mk_f(e)
         self.e1_to_e2, self.e1_to_e3 = mk_i(e), mk_i(e)
         self.e2_src, self.e2_dst, self.e2_rel, self.e2_val = mk_i(e), mk_i(e), mk_i(e), mk_f(e)
         self.e2_to_e3 = mk_i(e)
         self.e3_src, self.e3_dst, self.e3_val, self.e3_to_e2 = mk_i(e), mk_i(e), mk_f(e), mk_i(e)
         self.long_rows = self.long_cols = None
-        self.chunk_rel = self.chunk_ptr = self.rel_chunk_ptr = None
+        self.chunk_rel = self.chunk_ptr = self.rel_chunk_ptr = self.rel_chunk_idx = None
         self.n_chunks = 0
         self.c = nv.Graph()
 
@@ -52,6 +55,7 @@ class RelGraph:
     def _fill_struct(self):
         c = self.c
         c.E, c.ND, c.NS, c.R = self.E, self.ND, self.NS, self.R
+        c.slab_rows = self.slab_rows
         for name in ("rowptr", "e1_src", "e1_rel", "e1_val", "e1_to_e2", "e1_to_e3", "colptr", "e2_src", "e2_dst",
                      "e2_rel", "e2_val", "e2_to_e3", "relptr", "e3_src", "e3_dst", "e3_val", "e3_to_e2"):
             setattr(c, name, getattr(self, name).data_ptr())
@@ -73,28 +77,35 @@ class RelGraph:
             return mk(hub if len(hub) else [0]), mk(first), int(first[-1])
         self.row_seg_hub, self.row_seg_first, self.n_row_segs = segments(deg_r, self.long_rows)
         self.col_seg_hub, self.col_seg_first, self.n_col_segs = segments(deg_c, self.long_cols)
-        relptr = self.relptr.cpu().numpy().astype(np.int64)
+        relptr = self.relptr.cpu().numpy().astype(np.int64)          # groups g = slab*R + rel
         ch = chunk or _chunk_size(self.E)
+        ngrp = len(relptr) - 1
         cnt = np.diff(relptr)
         nch = (cnt + ch - 1) // ch
-        rel_chunk_ptr = np.zeros(self.R + 1, dtype=np.int64)
-        np.cumsum(nch, out=rel_chunk_ptr[1:])
-        n_chunks = int(rel_chunk_ptr[-1])
-        chunk_rel = np.repeat(np.arange(self.R), nch)
-        within = np.arange(n_chunks) - rel_chunk_ptr[chunk_rel]
-        lo = relptr[chunk_rel] + within * ch
+        grp_chunk_ptr = np.zeros(ngrp + 1, dtype=np.int64)
+        np.cumsum(nch, out=grp_chunk_ptr[1:])
+        n_chunks = int(grp_chunk_ptr[-1])
+        chunk_grp = np.repeat(np.arange(ngrp), nch)
+        within = np.arange(n_chunks) - grp_chunk_ptr[chunk_grp]
+        lo = relptr[chunk_grp] + within * ch
         chunk_ptr = np.empty(n_chunks + 1, dtype=np.int64)
         chunk_ptr[:-1] = lo
         chunk_ptr[-1] = relptr[-1]
-        # a chunk ends where the next begins or where its relation ends
-        if n_chunks:
-            hi = np.minimum(lo + ch, relptr[chunk_rel + 1])
+        if n_chunks:     # a chunk ends where the next begins or where its group ends
+            hi = np.minimum(lo + ch, relptr[chunk_grp + 1])
             assert np.array_equal(hi[:-1], chunk_ptr[1:-1]) and hi[-1] == chunk_ptr[-1]
+        chunk_rel = chunk_grp % self.R
+        # chunks of one relation (scattered over the slabs), in slab order: a fixed reduction order
+        order = np.argsort(chunk_rel, kind="stable")
+        rel_chunk_ptr = np.zeros(self.R + 1, dtype=np.int64)
+        np.cumsum(np.bincount(chunk_rel, minlength=self.R), out=rel_chunk_ptr[1:])
         self.chunk_size = ch
         self.n_chunks = n_chunks
-        self.chunk_rel = torch.from_numpy(chunk_rel.astype(np.int32)).to(dev) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
-        self.chunk_ptr = torch.from_numpy(chunk_ptr.astype(np.int32)).to(dev)
-        self.rel_chunk_ptr = torch.from_numpy(rel_chunk_ptr.astype(np.int32)).to(dev)
+        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        self.chunk_rel = mk(chunk_rel) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
+        self.chunk_ptr = mk(chunk_ptr)
+        self.rel_chunk_ptr = mk(rel_chunk_ptr)
+        self.rel_chunk_idx = mk(order) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
         c = self.c
         c.long_rows = self.long_rows.data_ptr() if len(self.long_rows) else None
         c.n_long_rows, c.long_row_thresh = len(self.long_rows), LONG_THRESH
@@ -105,6 +116,7 @@ class RelGraph:
         c.n_row_segs, c.n_col_segs, c.long_seg = self.n_row_segs, self.n_col_segs, LONG_SEG
         c.chunk_rel, c.chunk_ptr = self.chunk_rel.data_ptr(), self.chunk_ptr.data_ptr()
         c.rel_chunk_ptr, c.n_chunks = self.rel_chunk_ptr.data_ptr(), n_chunks
+        c.rel_chunk_idx = self.rel_chunk_idx.data_ptr()
 
     # ------------------------------------------------------------------------------------------
     @classmethod
