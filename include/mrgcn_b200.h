@@ -129,7 +129,9 @@ int mrgcn_adjacency_from_triples(const int32_t *triples, int64_t T, int32_t N, i
  * addend [ND,out] or NULL: a pre-activation term computed elsewhere (the identity term of a node-partitioned
  *   run, after its reduce-scatter).  Its gradient is `gact` of the backward call.
  * wmix: workspace [R*in*out] (only if B>0 and X given; receives W_F(r), needed by backward)
- * msg_I: workspace [E_I*out] (only if B>0 and weight_I given); msg_F: workspace [E_F*out]. */
+ * msg_I: workspace [E_I*mrgcn_msg_stride(out)] (only if B>0 and weight_I given); msg_F: workspace
+ * [E_F*mrgcn_msg_stride(out)] (per-edge messages, rows padded to 16-byte multiples). */
+int32_t mrgcn_msg_stride(int32_t out);
 typedef struct mrgcn_layer_args {
   const mrgcn_graph *gI, *gF;
   int32_t in_dim, out_dim, B, relu;
@@ -154,7 +156,7 @@ typedef struct mrgcn_layer_bwd_args {
   float *g_weight_I, *g_comp_I, *g_weight_F, *g_comp_F, *g_bias, *g_X;
   float *gact, *cbuf, *part, *g_wmix, *colsum_ws;
   float *wt_ws;   /* [R*in*out]  (g_X wanted) transposed weights */
-  float *msgx_ws; /* [E_F*in]    (g_X wanted) per-edge input-gradient messages */
+  float *msgx_ws; /* [E_F*mrgcn_msg_stride(in)] (g_X wanted) per-edge input-gradient messages */
 } mrgcn_layer_bwd_args;
 int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_t stream);
 

@@ -165,10 +165,10 @@ k_feat_msg_tc(const float *__restrict__ X, const float *__restrict__ W, const in
         const int e = e0 + warp * 32 + lane;
         if (e < e_hi && !(dbg & 4)) {
           const float v = val[e];
-          float *mp = msg + (size_t)e * out;
+          const int ms = msg_stride(out);
 #pragma unroll
-          for (int o = 0; o < NP; ++o)
-            if (o < out) mp[o] = v * d[o];
+          for (int o = 0; o < NP; ++o) d[o] *= v;
+          store_msg_chunk<NP>(msg + (size_t)e * ms, 0, out, ms, d);
         }
       }
     }

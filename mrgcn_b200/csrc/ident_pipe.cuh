@@ -37,36 +37,38 @@ __device__ __forceinline__ void ident_pipeline(const IdentPipe &p, const float *
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S;
   if (warp == kPipeConsumerWarps) {
-    // ===== producer (one elected lane) =====
-    if (lane == 0) {
-      const uint32_t run_bytes = (uint32_t)p.TJ * p.out * 4;
-      for (int k = 0;; ++k) {
-        const int t = blockIdx.x + k * gridDim.x;
-        if (t >= p.ntiles) break;
-        const int s = k % S;
-        int j0 = t * p.TJ;
-        if (j0 + p.TJ > p.NS) j0 = p.NS - p.TJ;
-        const int e_lo = colptr[j0], e_hi = colptr[j0 + p.TJ];
-        const int a_lo = e_lo & ~3;
-        int cnt = min(e_hi - a_lo, p.mcap);
-        cnt = e_hi > e_lo ? ((cnt + 3) & ~3) : 0;
-        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, 7);  // stage drained by every consumer warp
-        unsigned char *st = stage_base + (size_t)s * p.stage_bytes;
+    // ===== producer warp: lane 0 owns the barriers, all 32 lanes issue bulk copies (one thread alone cannot issue
+    //       B + 3 small copies per tile fast enough to keep HBM busy) =====
+    const uint32_t run_bytes = (uint32_t)p.TJ * p.out * 4;
+    for (int k = 0;; ++k) {
+      const int t = blockIdx.x + k * gridDim.x;
+      if (t >= p.ntiles) break;
+      const int s = k % S;
+      int j0 = t * p.TJ;
+      if (j0 + p.TJ > p.NS) j0 = p.NS - p.TJ;
+      const int e_lo = colptr[j0], e_hi = colptr[j0 + p.TJ];
+      const int a_lo = e_lo & ~3;
+      int cnt = min(e_hi - a_lo, p.mcap);
+      cnt = e_hi > e_lo ? ((cnt + 3) & ~3) : 0;
+      unsigned char *st = stage_base + (size_t)s * p.stage_bytes;
+      float *vs = reinterpret_cast<float *>(st + 16);
+      int *mA = reinterpret_cast<int *>(st + 16 + (size_t)p.v_floats * 4);
+      int *mB = mA + p.mcap + 4;
+      float *mC = reinterpret_cast<float *>(mB + p.mcap + 4);
+      if (lane == 0) {
+        mbar_wait(&empty[s], ((k / S) & 1) ^ 1, 7);   // stage drained by every consumer warp
         int *hdr = reinterpret_cast<int *>(st);
         hdr[0] = e_lo; hdr[1] = e_hi; hdr[2] = j0; hdr[3] = a_lo;
-        float *vs = reinterpret_cast<float *>(st + 16);
-        int *mA = reinterpret_cast<int *>(st + 16 + (size_t)p.v_floats * 4);
-        int *mB = mA + p.mcap + 4;
-        float *mC = reinterpret_cast<float *>(mB + p.mcap + 4);
         fence_proxy_async();
         mbar_expect_tx(&full[s], run_bytes * p.B + 3u * cnt * 4u);
-        for (int b = 0; b < p.B; ++b)
-          bulk_g2s(vs + (size_t)b * p.TJ * p.out, V + ((size_t)b * p.NS + j0) * p.out, run_bytes, &full[s]);
-        if (cnt > 0) {
-          bulk_g2s(mA, gA + a_lo, cnt * 4u, &full[s]);
-          bulk_g2s(mB, gB + a_lo, cnt * 4u, &full[s]);
-          bulk_g2s(mC, gC + a_lo, cnt * 4u, &full[s]);
-        }
+      }
+      __syncwarp();
+      for (int b = lane; b < p.B; b += 32)
+        bulk_g2s(vs + (size_t)b * p.TJ * p.out, V + ((size_t)b * p.NS + j0) * p.out, run_bytes, &full[s]);
+      if (cnt > 0) {
+        if (lane == 29) bulk_g2s(mA, gA + a_lo, cnt * 4u, &full[s]);
+        if (lane == 30) bulk_g2s(mB, gB + a_lo, cnt * 4u, &full[s]);
+        if (lane == 31) bulk_g2s(mC, gC + a_lo, cnt * 4u, &full[s]);
       }
     }
     return;

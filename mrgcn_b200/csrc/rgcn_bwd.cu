@@ -879,7 +879,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         if (gF->E > 0)
           if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
         AggArgs g{};
-        g.ND = (int)NS; g.odim = in; g.out = a->g_X;
+        g.ND = (int)NS; g.odim = in; g.ms = msg_stride(in); g.out = a->g_X;
         g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;
         g.thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
         HubSegs hs{gF->long_cols, gF->col_seg_hub, gF->col_seg_first, gF->n_long_cols, gF->n_col_segs, gF->long_seg, f.hub_ws};

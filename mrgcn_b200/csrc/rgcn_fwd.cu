@@ -83,15 +83,15 @@ __device__ __forceinline__ void ident_msg_tile(const float *__restrict__ Vs, siz
     const int jl = e2_src[e] - j0, r = e2_rel[e];
     const float v = e2_val[e];
     const float *cr = comp_s ? comp_s + r * CS : comp + (size_t)r * B;
-    for (int c0 = 0; c0 < out; c0 += OC) {
+    const int ms = msg_stride(out);
+    for (int c0 = 0; c0 < ms; c0 += OC) {
       float acc[OC];
 #pragma unroll
       for (int o = 0; o < OC; ++o) acc[o] = 0.f;
-      mix_bases<OC, VW>(Vs + (size_t)jl * RS + c0, bstride, cr, B, acc);
-      float *mp = msg + (size_t)e * out + c0;
+      if (c0 < out) mix_bases<OC, VW>(Vs + (size_t)jl * RS + c0, bstride, cr, B, acc);
 #pragma unroll
-      for (int o = 0; o < OC; ++o)
-        if (c0 + o < out) mp[o] = v * acc[o];
+      for (int o = 0; o < OC; ++o) acc[o] *= v;
+      store_msg_chunk<OC>(msg + (size_t)e * ms, c0, out, ms, acc);
     }
   }
 }
@@ -127,15 +127,15 @@ k_ident_msg_fwd_bulk(const float *__restrict__ V, const float *__restrict__ comp
                  [&](const float *vs, int j0, int e, int src, int rel, float v) {
                    const float *cr = comp_s + rel * CS;
                    const float *vrow = vs + (size_t)(src - j0) * out;
-                   for (int c0 = 0; c0 < out; c0 += OC) {
+                   const int ms = msg_stride(out);
+                   for (int c0 = 0; c0 < ms; c0 += OC) {
                      float acc[OC];
 #pragma unroll
                      for (int o = 0; o < OC; ++o) acc[o] = 0.f;
-                     mix_bases<OC, VW>(vrow + c0, bstride, cr, B, acc);
-                     float *mp = msg + (size_t)e * out + c0;
+                     if (c0 < out) mix_bases<OC, VW>(vrow + c0, bstride, cr, B, acc);
 #pragma unroll
-                     for (int o = 0; o < OC; ++o)
-                       if (c0 + o < out) mp[o] = v * acc[o];
+                     for (int o = 0; o < OC; ++o) acc[o] *= v;
+                     store_msg_chunk<OC>(msg + (size_t)e * ms, c0, out, ms, acc);
                    }
                  });
 }
@@ -254,12 +254,13 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
       }
       if (live) {
         const float v = e3_val[e];
-        float *mp = msg + (size_t)e * out + c0;
+        const int ms = msg_stride(out);
+        float vals[OC];
 #pragma unroll
-        for (int o = 0; o < OC / 2; ++o) {
-          if (c0 + 2 * o < out) mp[2 * o] = v * acc[o].x;
-          if (c0 + 2 * o + 1 < out) mp[2 * o + 1] = v * acc[o].y;
-        }
+        for (int o = 0; o < OC / 2; ++o) { vals[2 * o] = v * acc[o].x; vals[2 * o + 1] = v * acc[o].y; }
+        store_msg_chunk<OC>(msg + (size_t)e * ms, c0, out, ms, vals);
+        if (c0 + OC >= out)   // last computed chunk: zero the rest of the padded row
+          for (int o = c0 + OC; o < ms; o += 4) *reinterpret_cast<float4 *>(msg + (size_t)e * ms + o) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -337,7 +338,12 @@ k_feat_msg_rw(const float *__restrict__ X, const float *__restrict__ W, const in
     }
     const int g = lane / OC, o = lane - g * OC;
     const int e = e0 + g;
-    if (g < EG && o < out && e < e_hi) msg[(size_t)e * out + o] = __ldg(e3_val + e) * v[0];
+    const int ms = msg_stride(out);
+    if (g < EG && e < e_hi) {
+      msg[(size_t)e * ms + o] = o < out ? __ldg(e3_val + e) * v[0] : 0.f;
+      if (o == 0)
+        for (int z = OC; z < ms; ++z) msg[(size_t)e * ms + z] = 0.f;
+    }
   }
 }
 
@@ -346,7 +352,7 @@ k_feat_msg_rw(const float *__restrict__ X, const float *__restrict__ W, const in
 
 // sum of msg[perm[e]][o] over e = lo+beg, lo+beg+step, ... < hi; four gathers in flight, fixed order
 __device__ __forceinline__ float gather_sum(const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi,
-                                            int beg, int step, int od, int o, float acc) {
+                                            int beg, int step, int od /* row stride */, int o, float acc) {
   int e = lo + beg;
   for (; e + 3 * step < hi; e += 4 * step) {
     const int p0 = perm[e], p1 = perm[e + step], p2 = perm[e + 2 * step], p3 = perm[e + 3 * step];
@@ -365,7 +371,7 @@ __device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int b
   if (a.rowptr) {
     int lo = a.rowptr[i], hi = a.rowptr[i + 1];
     if (len >= 0) { lo = min(hi, lo + off); hi = min(hi, lo + len); }
-    if (a.msgI) acc = gather_sum(a.msgI, a.pI, lo, hi, beg, step, od, o, acc);
+    if (a.msgI) acc = gather_sum(a.msgI, a.pI, lo, hi, beg, step, a.ms, o, acc);
     if (a.Wd) {
       int e = lo + beg;
       for (; e + step < hi; e += 2 * step) {
@@ -380,7 +386,7 @@ __device__ __forceinline__ float agg_edges(const AggArgs &a, int i, int o, int b
   if (a.msgF) {
     int lo = a.rowptrF[i], hi = a.rowptrF[i + 1];
     if (len >= 0) { lo = min(hi, lo + off); hi = min(hi, lo + len); }
-    acc = gather_sum(a.msgF, a.pF, lo, hi, beg, step, od, o, acc);
+    acc = gather_sum(a.msgF, a.pF, lo, hi, beg, step, a.ms, o, acc);
   }
   return acc;
 }
@@ -418,6 +424,59 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
     if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
     agg_store(a, i, o, agg_edges(a, i, o, 0, 1));
   }
+}
+
+// short rows, vector variant: MS/4 lanes per row, each lane owns 4 consecutive outputs and gathers 16-byte pieces of the
+// (64-byte aligned) message rows; four gathers in flight; fixed order.
+__device__ __forceinline__ void gather_sum4(const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi,
+                                            int ms, int o0, float4 &acc) {
+  int e = lo;
+  for (; e + 3 < hi; e += 4) {
+    const int p0 = perm[e], p1 = perm[e + 1], p2 = perm[e + 2], p3 = perm[e + 3];
+    const float4 v0 = *reinterpret_cast<const float4 *>(msg + (size_t)p0 * ms + o0);
+    const float4 v1 = *reinterpret_cast<const float4 *>(msg + (size_t)p1 * ms + o0);
+    const float4 v2 = *reinterpret_cast<const float4 *>(msg + (size_t)p2 * ms + o0);
+    const float4 v3 = *reinterpret_cast<const float4 *>(msg + (size_t)p3 * ms + o0);
+    acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+    acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+    acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+    acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+  }
+  for (; e < hi; ++e) {
+    const float4 v = *reinterpret_cast<const float4 *>(msg + (size_t)perm[e] * ms + o0);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_agg_fwd_v4(AggArgs a) {
+  const int od = a.odim, ms = a.ms;
+  const int G = ms >> 2;                       // lanes per row (1, 2, 4, 8, ...)
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int rpw = 32 / G;
+  const int slot = lane / G, o0 = (lane - slot * G) * 4;
+  const int i = gw * rpw + slot;
+  if (i >= a.ND || o0 >= od) return;
+  if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.rowptr) {
+    const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+    if (a.msgI) gather_sum4(a.msgI, a.pI, lo, hi, ms, o0, acc);
+    if (a.Wd) {
+      for (int e = lo; e < hi; ++e) {
+        const float *wr = a.Wd + ((size_t)a.d_rel[e] * a.NSd + a.d_src[e]) * od + o0;
+        const float v = a.d_val[e];
+        acc.x = fmaf(v, wr[0], acc.x);
+        if (o0 + 1 < od) acc.y = fmaf(v, wr[1], acc.y);
+        if (o0 + 2 < od) acc.z = fmaf(v, wr[2], acc.z);
+        if (o0 + 3 < od) acc.w = fmaf(v, wr[3], acc.w);
+      }
+    }
+  }
+  if (a.msgF) gather_sum4(a.msgF, a.pF, a.rowptrF[i], a.rowptrF[i + 1], ms, o0, acc);
+  agg_store(a, i, o0, acc.x);
+  if (o0 + 1 < od) agg_store(a, i, o0 + 1, acc.y);
+  if (o0 + 2 < od) agg_store(a, i, o0 + 2, acc.z);
+  if (o0 + 3 < od) agg_store(a, i, o0 + 3, acc.w);
 }
 
 // hubs: one CTA (1024 threads) per SEGMENT of a long row; edge slots strided over the segment, fixed-order tree over
@@ -637,10 +696,16 @@ int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X,
 
 int launch_agg(const AggArgs &g, const HubSegs &h, cudaStream_t st, const char *prof_name) {
   if (g.ND <= 0) return 0;
-  const int rows_per_warp = g.odim >= 32 ? 1 : 32 / g.odim;
-  unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
   mrgcn::prof_begin(prof_name, st);
-  k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
+  if (g.ms <= 128) {
+    const int rows_per_warp = 32 / (g.ms >> 2);
+    unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
+    k_agg_fwd_v4<<<grid, kThreads, 0, st>>>(g);
+  } else {
+    const int rows_per_warp = g.odim >= 32 ? 1 : 32 / g.odim;
+    unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
+    k_agg_fwd<<<grid, kThreads, 0, st>>>(g);
+  }
   MRGCN_LAUNCH_CHECK();
   if (h.n_long > 0) {
     MRGCN_REQUIRE(h.ws || h.n_segs == h.n_long, MRGCN_E_BADARG, "agg: hub_ws missing");
@@ -660,6 +725,8 @@ int launch_agg(const AggArgs &g, const HubSegs &h, cudaStream_t st, const char *
 
 using namespace mrgcn;
 
+extern "C" int32_t mrgcn_msg_stride(int32_t out) { return msg_stride(out); }
+
 extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MRGCN_REQUIRE(a && a->out && a->out_dim > 0, MRGCN_E_BADARG, "layer_fwd: null/empty output");
@@ -673,7 +740,7 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
   MRGCN_REQUIRE(!(hasI && hasF) || gI->ND == gF->ND, MRGCN_E_BADARG, "layer_fwd: graphs disagree on rows");
 
   AggArgs g{};
-  g.ND = ND; g.odim = out; g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.addend = a->addend; g.out = a->out;
+  g.ND = ND; g.odim = out; g.ms = msg_stride(out); g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.addend = a->addend; g.out = a->out;
   const mrgcn_graph *gl = hasI ? gI : gF;  // long-row list owner
   if (hasI) {
     g.rowptr = gI->rowptr;

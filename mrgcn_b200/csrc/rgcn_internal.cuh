@@ -4,6 +4,28 @@
 
 namespace mrgcn {
 
+// Row stride (floats) of per-edge message buffers: rows are padded so that a row never straddles a 64-byte DRAM
+// access granule more than necessary and can be moved with 16-byte vector accesses (pads are written as zeros).
+__host__ __device__ inline int msg_stride(int out) { return out <= 4 ? 4 : out <= 8 ? 8 : ((out + 15) / 16) * 16; }
+
+// store one OC-wide chunk [c0, c0+OC) of a message row (row stride ms), zero beyond `out`, nothing beyond ms
+template <int OC>
+__device__ __forceinline__ void store_msg_chunk(float *__restrict__ row, int c0, int out, int ms, const float (&val)[OC]) {
+  if constexpr (OC % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < OC / 4; ++q) {
+      const int o = c0 + 4 * q;
+      if (o < ms)
+        *reinterpret_cast<float4 *>(row + o) = make_float4(o < out ? val[4 * q] : 0.f, o + 1 < out ? val[4 * q + 1] : 0.f,
+                                                           o + 2 < out ? val[4 * q + 2] : 0.f, o + 3 < out ? val[4 * q + 3] : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < OC; ++q)
+      if (c0 + q < ms) row[c0 + q] = c0 + q < out ? val[q] : 0.f;
+  }
+}
+
 // Arguments of the segmented message aggregation (rows = destinations in forward, sources in the input-gradient pass).
 struct AggArgs {
   const int32_t *rowptr;
@@ -17,6 +39,7 @@ struct AggArgs {
   const float *d_val;
   int64_t NSd;
   const float *bias, *mask, *addend;
+  int ms;              // row stride of msgI / msgF (msg_stride(odim))
   float *out;
   int ND, odim, relu, thresh;
 };

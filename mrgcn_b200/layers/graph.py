@@ -50,8 +50,9 @@ class _LayerFn(torch.autograd.Function):
             raise ValueError("weight_I has %d rows, expected %d" % (weight_I.shape[0], (B if B else gI.R) * gI.NS))
         out = torch.empty((g0.ND, out_dim), dtype=torch.float32, device=dev)
         wmix = _empty(gF.R * in_dim * out_dim, dev) if (hasF and B) else None
-        msg_I = _empty(gI.E * out_dim, dev) if (hasI and B) else None
-        msg_F = _empty(gF.E * out_dim, dev) if hasF else None
+        ms = int(nv.lib().mrgcn_msg_stride(out_dim))
+        msg_I = _empty(gI.E * ms, dev) if (hasI and B) else None
+        msg_F = _empty(gF.E * ms, dev) if hasF else None
         a = nv.LayerArgs()
         a.gI = C.pointer(gI.c) if hasI else None
         a.gF = C.pointer(gF.c) if hasF else None
@@ -107,7 +108,7 @@ class _LayerFn(torch.autograd.Function):
         if hasF and need[0]:
             g_X = torch.empty_like(X)
             wt_ws = _empty(gF.R * in_dim * out_dim, dev)
-            msgx_ws = _empty(gF.E * in_dim, dev)
+            msgx_ws = _empty(gF.E * int(nv.lib().mrgcn_msg_stride(in_dim)), dev)
         colsum = None
         if bias is not None and need[5]:
             g_b = torch.empty_like(bias)
