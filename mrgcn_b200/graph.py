@@ -19,7 +19,8 @@ import torch
 from . import _native as nv
 
 LONG_THRESH = 128      # rows / sources with more edges than this ("hubs") are handled by CTAs of their own
-SLAB_ROWS = 32768      # sources per slab of the relation-major order (a slab of feature rows stays L2-resident)
+SLAB_ROWS = 32768      # minimum sources per slab of the relation-major order (a slab of feature rows stays L2-resident)
+SLAB_GROUP_EDGES = 1024  # ... grown until a (slab, relation) group holds about this many edges on average
 LONG_SEG = 512         # ... one CTA per segment of this many edges; partial sums combined in segment order
 _I32 = torch.int32
 
@@ -38,7 +39,13 @@ class RelGraph:
         e = self.E + 8          # slack: the TMA-engine kernels copy edge ranges rounded up to 16 bytes
         mk_i = lambda n: torch.empty(n, dtype=_I32, device=device)
         mk_f = lambda n: torch.empty(n, dtype=torch.float32, device=device)
-        self.slab_rows = SLAB_ROWS
+        # slabs as small as L2 residency wants, but not so small that the (slab, relation) groups -- the unit of the
+        # relation-major kernels -- degenerate (sparse shards of a partitioned graph)
+        want = SLAB_ROWS
+        if self.E > 0:
+            while want < NS and (NS // want + 1) * R * SLAB_GROUP_EDGES > self.E:
+                want *= 2
+        self.slab_rows = int(want)
         self.n_slabs = max(1, -(-NS // self.slab_rows))
         self.rowptr, self.colptr, self.relptr = mk_i(ND + 1), mk_i(NS + 1), mk_i(self.n_slabs * R + 1)
         self.e1_src, self.e1_rel, self.e1_val = mk_i(e), mk_i(e), mk_f(e)

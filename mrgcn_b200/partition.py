@@ -89,6 +89,11 @@ def _reduce_scatter_rows(full, lay):
     return out[:lay.sizes[lay.rank]]
 
 
+def gather_rows(x, lay):
+    """All-gather row blocks (no autograd): rank p contributes rows [bounds[p], bounds[p+1])."""
+    return _all_gather_rows(x.contiguous(), lay)
+
+
 class GatherRows(torch.autograd.Function):
     """local rows (n_p, d) -> all rows (N, d); backward: reduce-scatter of the gradient."""
 
