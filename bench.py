@@ -436,7 +436,13 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A captured CUDA graph holds NCCL kernels of this communicator; tearing the process group down with the graph
+        # alive can block.  Everything has been measured and printed: drain, meet the other ranks, leave.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
