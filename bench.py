@@ -411,9 +411,17 @@ def main():
                                  "alg_gb_per_step": gb, "gbps": (gb / (ms / args.steps / 1e3)) if gb else None}
             top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
             k = kernels[top]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tpath) and args.shape == "am" and args.scale == 1.0 and world == 1:
+                with open(tpath) as f:
+                    t = json.load(f).get(top)
+                if t and k["launches_per_step"]:
+                    traffic = t["bytes_per_step"] / k["launches_per_step"]      # per launch, like `achieved`
             if k["gbps"]:
                 roof = {"kernel": top, "bound": "hbm", "achieved": k["gbps"], "peak": peak, "unit": "GB/s",
-                        "frac": k["gbps"] / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": k["gbps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                        "alg_bytes_per_launch": k["alg_gb_per_step"] * 1e9 / max(k["launches_per_step"], 1),
                         "launches_per_step": k["launches_per_step"], "ms_per_step": k["ms_per_step"], "share_of_step": k["share"],
                         "step_alg_gb": sum(v["alg_gb_per_step"] or 0 for v in kernels.values()),
                         "step_gbps": sum(v["alg_gb_per_step"] or 0 for v in kernels.values()) / (ms_step / 1e3)}
