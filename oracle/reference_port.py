@@ -184,6 +184,29 @@ def rgcn_forward(layers, activations, X, A, *, num_nodes, num_relations, num_bas
 
 
 # --------------------------------------------------------------------------------------
+# MRGCN: gated scatter of literal-encoder outputs  (mrgcn/models/mrgcn.py:189-214,250-305)
+# --------------------------------------------------------------------------------------
+def mlp_forward(weights, x):
+    """mrgcn/models/perceptron.py:6-46 with p_dropout = 0: Linear -> (Dropout) -> ReLU per layer.
+    weights: [(W, b), ...] in layer order."""
+    for W, b in weights:
+        x = torch.relu(torch.nn.functional.linear(x, W, b))
+    return x
+
+
+def modality_features(num_nodes, sets, gate_weights):
+    """mrgcn.py:250-305 for a full batch: zeros (N, sum dim); per encoding set (in order) the encoder output times its
+    gate weight is written into the rows listed in node_idx.  sets: [(mlp_weights, encodings, node_idx), ...]."""
+    cols = []
+    for i, (weights, enc, node_idx) in enumerate(sets):
+        out = mlp_forward(weights, enc.float()) * gate_weights[i]
+        block = torch.zeros((num_nodes, out.shape[1]), dtype=torch.float32)
+        block = block.index_put((torch.as_tensor(node_idx),), out)
+        cols.append(block)
+    return torch.cat(cols, dim=1)
+
+
+# --------------------------------------------------------------------------------------
 # link prediction  (mrgcn/tasks/link_prediction.py)
 # --------------------------------------------------------------------------------------
 def distmult_score(idx, node_emb, rel_emb):

@@ -209,6 +209,34 @@ def case_minibatch(tr, N, P, Af):
          grad_X=Xo.grad.numpy(), meta=np.array([R, N, 2]), **arrs)
 
 
+def case_mrgcn_modalities(tr, N, P, Af):
+    """MRGCN.forward with gated literal encoders (mrgcn.py:189-214,250-305): numeric MLP + temporal MLP whose
+    outputs are scaled by gate_weights and scattered into the rows of the nodes that carry the literal."""
+    R = 2 * P + 1
+    torch.manual_seed(31)
+    rng = np.random.default_rng(31)
+    idx_num = np.sort(rng.choice(N, 23, replace=False))
+    idx_date = np.sort(rng.choice(N, 17, replace=False))
+    enc_num = rng.normal(size=(23, 3)).astype(np.float32)
+    enc_date = rng.normal(size=(17, 6)).astype(np.float32)
+    emb = [("xsd.numeric", (3, 2, 0.0), False), ("xsd.date", (6, 4, 0.0), False)]
+    modules = [(6, 5, "mrgcn", nn.ReLU()), (5, 3, "mrgcn", None)]
+    model = MRGCN(modules, emb, R, N, num_bases=2, p_dropout=0.0, featureless=False, bias=True)
+    X = [np.empty((N, 0), dtype=np.float32),
+         ["xsd.numeric", [[enc_num, idx_num, np.full(23, -1)]], False],
+         ["xsd.date", [[enc_date, idx_date, np.full(17, -1)]], False]]
+    fb = FullBatch(Af, X, np.arange(N))
+    fb.as_tensors_()
+    fb.A = torch.sparse_coo_tensor(fb.A._indices(), torch.Tensor(Af.data), Af.shape)
+    out = model(fb)
+    G = torch.randn_like(out)
+    (out * G).sum().backward()
+    arrs = {"param_" + k: v.detach().numpy().copy() for k, v in model.named_parameters()}
+    arrs.update(grads(model.named_parameters()))
+    save("mrgcn_modalities", out=out.detach().numpy(), G=G.numpy(), idx_num=idx_num, idx_date=idx_date, enc_num=enc_num,
+         enc_date=enc_date, meta=np.array([R, N, 2]), **arrs)
+
+
 def case_distmult():
     torch.manual_seed(9)
     E = torch.randn(50, 24, requires_grad=True)
@@ -246,6 +274,7 @@ def main():
             k += 1
     case_rgcn(tr, N, P, Af)
     case_minibatch(tr, N, P, Af)
+    case_mrgcn_modalities(tr, N, P, Af)
     case_distmult()
 
 

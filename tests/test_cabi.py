@@ -63,3 +63,34 @@ def test_product_does_not_import_oracle():
                           "print(any(m.startswith('oracle') for m in sys.modules))" % ROOT],
                          check=True, capture_output=True, text=True).stdout.strip()
     assert out == "False"
+
+
+def test_layer_init_matches_reference(golden):
+    """Same shapes, registration order and initialisers as the reference layer: the same seed gives the same
+    initial state_dict (graph.py:9-60,104-116).  Construction works without a GPU."""
+    import torch
+    from mrgcn_b200.layers.graph import GraphConvolution
+    g = golden("layer_input_features_b3")
+    indim, outdim, R, N, nb, bias, inp, fl = (int(v) for v in g["meta"])
+    torch.manual_seed(201)          # tests/golden/make_golden.py: seed 200 + k, k = 1 for (float values, 3 bases)
+    layer = GraphConvolution(indim, outdim, R, N, num_bases=nb, bias=bool(bias), input_layer=bool(inp), featureless=bool(fl))
+    assert [k for k, _ in layer.named_parameters()] == ["weight_I_comp", "weight_F_comp", "weight_I", "weight_F", "b"]
+    for k in ("weight_I_comp", "weight_F_comp", "weight_I", "weight_F"):
+        assert torch.equal(getattr(layer, k).detach(), torch.from_numpy(g["param_" + k])), k
+
+
+def test_model_state_dict_keys_match_reference_layout():
+    """Checkpoints are plain state_dicts (run.py:230-236): names, order and shapes must be the reference's."""
+    import torch.nn as nn
+    from mrgcn_b200.models.mrgcn import MRGCN
+    m = MRGCN([(7, 6, "mrgcn", nn.ReLU()), (6, 3, "mrgcn", None)], [("xsd.numeric", (3, 2, 0.0), False)], 9, 61, num_bases=3,
+              featureless=False, bias=True, link_prediction=True)
+    keys = list(m.state_dict().keys())
+    assert keys == ["gate_weights", "module_dict.xsd_numeric_0.mlp.0.weight", "module_dict.xsd_numeric_0.mlp.0.bias",
+                    "rgcn.relations",
+                    "rgcn.layers.layer_0.weight_I_comp", "rgcn.layers.layer_0.weight_F_comp", "rgcn.layers.layer_0.weight_I",
+                    "rgcn.layers.layer_0.weight_F", "rgcn.layers.layer_0.b",
+                    "rgcn.layers.layer_1.weight_F_comp", "rgcn.layers.layer_1.weight_F", "rgcn.layers.layer_1.b"]
+    sd = m.state_dict()
+    assert tuple(sd["rgcn.layers.layer_0.weight_I"].shape) == (3 * 61, 6) and tuple(sd["rgcn.relations"].shape) == (9, 3)
+    assert m.devices["relational"].type in ("cuda", "cpu") and m.gate_map == {"xsd_numeric_0": 0}

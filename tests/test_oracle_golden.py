@@ -153,3 +153,33 @@ def test_distmult(golden):
         sb = rp.distmult_score((torch.arange(50).view(1, 50, 1).expand(4, 50, 1), p[:4].view(4, 1, 1),
                                 o[:4].view(4, 1, 1)), E, Rel)
     assert torch.equal(sb, torch.from_numpy(g["scores_bc"]))
+
+
+def _mlp_weights(g, prefix, req=False):
+    ws = []
+    k = 0
+    while "param_%s.mlp.%d.weight" % (prefix, k) in g:
+        ws.append((torch.from_numpy(g["param_%s.mlp.%d.weight" % (prefix, k)]).requires_grad_(req),
+                   torch.from_numpy(g["param_%s.mlp.%d.bias" % (prefix, k)]).requires_grad_(req)))
+        k += 3          # Linear, Dropout, ReLU triplets (perceptron.py:31-34)
+    return ws
+
+
+def test_mrgcn_modalities(golden):
+    """MRGCN.forward with gated numeric + temporal encoders (mrgcn.py:189-214,250-305)."""
+    g, adj = golden("mrgcn_modalities"), golden("adjacency")
+    R, N, nb = (int(v) for v in g["meta"])
+    A = rp.csr_to_coo(rp.as_float32(rp.stacked_adjacency(adj["triples"], N, int(adj["num_props"]))), torch.float32)
+    gates = torch.from_numpy(g["param_gate_weights"]).requires_grad_(True)
+    sets = [(_mlp_weights(g, "module_dict.xsd_numeric_0", True), torch.from_numpy(g["enc_num"]), g["idx_num"]),
+            (_mlp_weights(g, "module_dict.xsd_date_0", True), torch.from_numpy(g["enc_date"]), g["idx_date"])]
+    X = rp.modality_features(N, sets, gates)
+    layers = []
+    for k in range(2):
+        pre = "param_rgcn.layers.layer_%d." % k
+        layers.append({n[len(pre):]: torch.from_numpy(v).requires_grad_(True) for n, v in g.items() if n.startswith(pre)})
+    out = rp.rgcn_forward(layers, ["relu", None], X, A, num_nodes=N, num_relations=R, num_bases=nb, featureless=False)
+    assert torch.equal(out.detach(), torch.from_numpy(g["out"]))
+    (out * torch.from_numpy(g["G"])).sum().backward()
+    assert torch.allclose(gates.grad, torch.from_numpy(g["grad_gate_weights"]), rtol=1e-6, atol=1e-7)
+    assert torch.equal(sets[0][0][0][0].grad, torch.from_numpy(g["grad_module_dict.xsd_numeric_0.mlp.0.weight"]))
