@@ -813,9 +813,9 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
     if (a->g_weight_F || a->g_comp_F) {
       float *gW = B > 0 ? a->g_wmix : a->g_weight_F;
       MRGCN_REQUIRE(gW && a->part, MRGCN_E_BADARG, "layer_bwd: g_wmix/part missing");
-      static int rw_mode = -1;
-      if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = !e ? 2 : (e[0] == '0' ? 0 : 1); }
-      if (gF->E > 0 && in <= 160 && out <= 16 && (rw_mode == 1 || (rw_mode == 2 && in > 64))) {
+      static int rw_mode = -1;   // MRGCN_FEAT_RW=0 selects the thread-per-row kernel everywhere
+      if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = (e && e[0] == '0') ? 0 : 1; }
+      if (gF->E > 0 && in <= 160 && out <= 16 && rw_mode == 1) {
         const int NK = (int)cdiv(in, 32);
         const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
         MRGCN_PROF("feat_bwd_w");

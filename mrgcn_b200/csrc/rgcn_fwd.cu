@@ -185,23 +185,25 @@ k_ident_msg_fwd(const float *__restrict__ V, const float *__restrict__ comp, con
 //       Xs[warp][2][32][KC+1]: rows of X for 32 edges, KC columns at a time, double buffered with cp.async
 //       (coalesced 128-byte row segments in flight while the previous segment is multiplied).
 constexpr int KC = 32;
-template <int OC>
+// KCT = columns staged per round: 32, or 16 for narrow inputs (in <= 16: hidden layers, input-gradient messages), where a
+// cp.async instruction then moves 16 columns of TWO rows so that no lane idles on zero padding.
+template <int OC, int KCT>
 __global__ void __launch_bounds__(kThreads)
 k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const int32_t *__restrict__ chunk_rel,
                const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ e3_src,
                const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {  // e3_src: gather index
   extern __shared__ __align__(16) float smem[];
   float *Ws = smem;                         // [INP][OC]
-  float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][2][32][KC+1]
+  float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][2][32][KCT+1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nwarps = kThreads / 32;
-  constexpr int XB = 32 * (KC + 1);
+  constexpr int XB = 32 * (KCT + 1);
   float *Xs = Xs_all + (size_t)warp * 2 * XB;
   const int c = blockIdx.x;
   const int r = chunk_rel[c];
   const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
   const float *Wr = W + (size_t)r * in * out;
-  const int nkc = INP / KC;
+  const int nkc = INP / KCT;
   for (int c0 = 0; c0 < out; c0 += OC) {
     __syncthreads();
     for (int x = tid; x < INP * OC; x += kThreads) {
@@ -214,13 +216,25 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
       const bool live = e < e_hi;
       const int j = live ? e3_src[e] : -1;
       auto prefetch = [&](int kc, int buf) {
-        float *dst = Xs + buf * XB + lane;
-        const int k = kc * KC + lane;
+        if constexpr (KCT == 32) {
+          float *dst = Xs + buf * XB + lane;
+          const int k = kc * KCT + lane;
 #pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int ji = __shfl_sync(0xffffffffu, j, i);
-          const bool ok = ji >= 0 && k < in;
-          cp_async4(dst + i * (KC + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+          for (int i = 0; i < 32; ++i) {
+            const int ji = __shfl_sync(0xffffffffu, j, i);
+            const bool ok = ji >= 0 && k < in;
+            cp_async4(dst + i * (KCT + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+          }
+        } else {
+          const int half = lane >> 4, col = lane & 15;
+          float *dst = Xs + buf * XB + col;
+          const int k = kc * KCT + col;
+#pragma unroll 8
+          for (int i = 0; i < 32; i += 2) {
+            const int ji = __shfl_sync(0xffffffffu, j, i + half);
+            const bool ok = ji >= 0 && k < in;
+            cp_async4(dst + (i + half) * (KCT + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+          }
         }
         cp_async_commit();
       };
@@ -237,10 +251,10 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
           cp_async_wait<0>();
         }
         __syncwarp();
-        const float *xrow = Xs + (kc & 1) * XB + lane * (KC + 1);
-        const float *wk = Ws + (size_t)kc * KC * OC;
+        const float *xrow = Xs + (kc & 1) * XB + lane * (KCT + 1);
+        const float *wk = Ws + (size_t)kc * KCT * OC;
 #pragma unroll 4
-        for (int kk = 0; kk < KC; ++kk) {
+        for (int kk = 0; kk < KCT; ++kk) {
           const float x = xrow[kk];
           const float4 *w4 = reinterpret_cast<const float4 *>(wk + kk * OC);
 #pragma unroll
@@ -673,22 +687,29 @@ int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X,
     return 0;
   }
   const int OC = pick_oc(out);
-  const int INP = (int)cdiv(in, KC) * KC;
-  size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 2 * 32 * (KC + 1)) * 4;
+  const int KCT = in <= 16 ? 16 : KC;
+  const int INP = (int)cdiv(in, KCT) * KCT;
+  size_t smem = ((size_t)INP * OC + (size_t)(kThreads / 32) * 2 * 32 * (KCT + 1)) * 4;
   MRGCN_REQUIRE(smem <= 220 * 1024, MRGCN_E_NOTSUP, "feat_msg: in too large for shared memory (%zu B)", smem);
-#define LAUNCH(OCV)                                                                                            \
-  do {                                                                                                         \
-    if (int rc = set_smem(k_feat_msg_fwd<OCV>, smem)) return rc;                                               \
-    k_feat_msg_fwd<OCV><<<(unsigned)g->n_chunks, kThreads, smem, st>>>(X, W, g->chunk_rel, g->chunk_ptr,      \
-                                                                      gather, g->e3_val, msg, in, out, INP);  \
+#define LAUNCH(OCV, KV)                                                                                            \
+  do {                                                                                                             \
+    if (int rc = set_smem(k_feat_msg_fwd<OCV, KV>, smem)) return rc;                                               \
+    k_feat_msg_fwd<OCV, KV><<<(unsigned)g->n_chunks, kThreads, smem, st>>>(X, W, g->chunk_rel, g->chunk_ptr,      \
+                                                                          gather, g->e3_val, msg, in, out, INP);  \
+  } while (0)
+#define LAUNCH_K(OCV)                 \
+  do {                                \
+    if (KCT == 16) LAUNCH(OCV, 16);   \
+    else LAUNCH(OCV, 32);             \
   } while (0)
   mrgcn::prof_begin(prof_name, st);
   switch (OC) {
-    case 4: LAUNCH(4); break;
-    case 8: LAUNCH(8); break;
-    case 12: LAUNCH(12); break;
-    default: LAUNCH(16); break;
+    case 4: LAUNCH_K(4); break;
+    case 8: LAUNCH_K(8); break;
+    case 12: LAUNCH_K(12); break;
+    default: LAUNCH_K(16); break;
   }
+#undef LAUNCH_K
 #undef LAUNCH
   MRGCN_LAUNCH_CHECK();
   return 0;
