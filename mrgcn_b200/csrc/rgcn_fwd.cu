@@ -281,87 +281,6 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Feature term, row-per-warp variant (in <= 160, out <= 16): the shared-memory variant above is bound by the
-// L1/shared data pipe (10 wavefronts per 32 (edge, k) products, ncu r01_feat).  Here W_r lives in REGISTERS
-// (lane l holds W[r][c*32+l][:] for every 32-wide k chunk c), a warp reads the feature row of an edge with NK
-// coalesced 128-byte loads straight into registers, multiplies, and the 32 per-lane partial sums of EG = 32/OC
-// edges x OC outputs are summed across lanes by a fixed halving tree of shuffles (lane L ends with slot L).
-// ~6x fewer shared-pipe wavefronts; no shared memory at all.
-template <int NK, int OC>
-__global__ void __launch_bounds__(kThreads, 2)
-k_feat_msg_rw(const float *__restrict__ X, const float *__restrict__ W, const int32_t *__restrict__ chunk_rel,
-              const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ gather,
-              const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out) {
-  constexpr int EG = 32 / OC;   // edges reduced together
-  constexpr int P = OC / 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
-  const int c = blockIdx.x;
-  const int r = chunk_rel[c];
-  const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
-  float2 w[NK][P];
-  {
-    const float *Wr = W + (size_t)r * in * out;
-#pragma unroll
-    for (int q = 0; q < NK; ++q) {
-      const int k = q * 32 + lane;
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        w[q][p].x = (k < in && 2 * p < out) ? __ldg(Wr + (size_t)k * out + 2 * p) : 0.f;
-        w[q][p].y = (k < in && 2 * p + 1 < out) ? __ldg(Wr + (size_t)k * out + 2 * p + 1) : 0.f;
-      }
-    }
-  }
-  for (int e0 = e_lo + warp * EG; e0 < e_hi; e0 += NW * EG) {
-    float x[EG][NK];
-#pragma unroll
-    for (int g = 0; g < EG; ++g) {
-      const int e = e0 + g;
-      const int j = e < e_hi ? __ldg(gather + e) : -1;   // uniform address: one transaction
-#pragma unroll
-      for (int q = 0; q < NK; ++q) {
-        const int k = q * 32 + lane;
-        x[g][q] = (j >= 0 && k < in) ? __ldg(X + (size_t)j * in + k) : 0.f;
-      }
-    }
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-#pragma unroll
-    for (int g = 0; g < EG; ++g) {
-      float2 acc[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < NK; ++q)
-#pragma unroll
-        for (int p = 0; p < P; ++p) fma2(acc[p], x[g][q], w[q][p]);
-#pragma unroll
-      for (int p = 0; p < P; ++p) { v[g * OC + 2 * p] = acc[p].x; v[g * OC + 2 * p + 1] = acc[p].y; }
-    }
-    // halving tree: after the step with mask m a lane keeps the half of the slots selected by its bit m
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int i = 0; i < m; ++i) {
-        const float send = up ? v[i] : v[i + m];
-        const float keep = up ? v[i + m] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-      }
-    }
-    const int g = lane / OC, o = lane - g * OC;
-    const int e = e0 + g;
-    const int ms = msg_stride(out);
-    if (g < EG && e < e_hi) {
-      msg[(size_t)e * ms + o] = o < out ? __ldg(e3_val + e) * v[0] : 0.f;
-      if (o == 0)
-        for (int z = OC; z < ms; ++z) msg[(size_t)e * ms + z] = 0.f;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Aggregation over destination rows (E1), fused with bias, row mask and ReLU (AggArgs: rgcn_internal.cuh).
 
 // sum of msg[perm[e]][o] over e = lo+beg, lo+beg+step, ... < hi; four gathers in flight, fixed order
@@ -572,7 +491,6 @@ int ident_tile(int B, int out, int OP) {
 }
 
 // tile of the TMA-engine variants: ~48 KB of V per stage, 16-byte runs; 0 = not applicable
-int ident_tile_bulk(int64_t NS, int out) { return (NS * out) % 4 == 0 ? 1 : 0; }
 int ident_pipe_config(IdentPipe &p, int64_t NS, int B, int out, size_t other_smem) {
   if ((NS * out) % 4 != 0) return 0;
   int tj = (48 * 1024) / (B * out * 4);
@@ -655,36 +573,6 @@ int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X,
     int launched = 0;
     if (int rc = launch_feat_msg_tc(g, gather, X, W, msg, in, out, st, prof_name, &launched)) return rc;
     if (launched) return 0;
-  }
-  // MRGCN_FEAT_RW=1 selects the row-per-warp variant; measured on AM it ties with the shared-memory variant in the
-  // forward direction (its shuffle tree costs what the shared-memory wavefronts cost), so it is off by default here
-  static int rw_mode = -1;
-  if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = (e && e[0] == '1') ? 1 : 0; }
-  if (in <= 160 && out <= 16 && rw_mode == 1) {   // row-per-warp variant: W_r in registers
-    const int NK = (int)cdiv(in, 32);
-    const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
-    mrgcn::prof_begin(prof_name, st);
-#define LAUNCH_RW(NKV, OCV) \
-  k_feat_msg_rw<NKV, OCV><<<(unsigned)g->n_chunks, kThreads, 0, st>>>(X, W, g->chunk_rel, g->chunk_ptr, gather, g->e3_val, msg, in, out)
-#define LAUNCH_NK(OCV)                  \
-  switch (NK) {                         \
-    case 1: LAUNCH_RW(1, OCV); break;   \
-    case 2: LAUNCH_RW(2, OCV); break;   \
-    case 3: LAUNCH_RW(3, OCV); break;   \
-    case 4: LAUNCH_RW(4, OCV); break;   \
-    default: LAUNCH_RW(5, OCV); break;  \
-  }
-    switch (OCR) {
-      case 4: LAUNCH_NK(4); break;
-      case 8: LAUNCH_NK(8); break;
-      case 10: LAUNCH_NK(10); break;
-      case 12: LAUNCH_NK(12); break;
-      default: LAUNCH_NK(16); break;
-    }
-#undef LAUNCH_NK
-#undef LAUNCH_RW
-    MRGCN_LAUNCH_CHECK();
-    return 0;
   }
   const int OC = pick_oc(out);
   const int KCT = in <= 16 ? 16 : KC;
