@@ -31,6 +31,39 @@ def _chunk_size(E):
     return int(min(1024, max(128, (ch // 32) * 32)))
 
 
+def chunk_worklist(grpptr, R, ch):
+    """Work list of the relation-major kernels.  grpptr: edge range of every group g = slab*R + rel (E3 order).
+    Every group is cut into chunks of at most `ch` edges (a chunk never crosses a group, hence holds one relation).
+    Returns (chunk_rel[n], chunk_ptr[n+1], rel_chunk_ptr[R+1], rel_chunk_idx[n]); rel_chunk_idx lists the chunks of
+    each relation in slab order, which fixes the order of the per-relation reductions."""
+    grpptr = np.asarray(grpptr, dtype=np.int64)
+    ngrp = len(grpptr) - 1
+    cnt = np.diff(grpptr)
+    nch = (cnt + ch - 1) // ch
+    grp_chunk_ptr = np.zeros(ngrp + 1, dtype=np.int64)
+    np.cumsum(nch, out=grp_chunk_ptr[1:])
+    n_chunks = int(grp_chunk_ptr[-1])
+    chunk_grp = np.repeat(np.arange(ngrp), nch)
+    within = np.arange(n_chunks) - grp_chunk_ptr[chunk_grp]
+    chunk_ptr = np.empty(n_chunks + 1, dtype=np.int64)
+    chunk_ptr[:-1] = grpptr[chunk_grp] + within * ch
+    chunk_ptr[-1] = grpptr[-1]
+    chunk_rel = chunk_grp % R
+    order = np.argsort(chunk_rel, kind="stable")
+    rel_chunk_ptr = np.zeros(R + 1, dtype=np.int64)
+    np.cumsum(np.bincount(chunk_rel, minlength=R), out=rel_chunk_ptr[1:])
+    return chunk_rel, chunk_ptr, rel_chunk_ptr, order
+
+
+def hub_segments(deg, seg):
+    """Hubs (rows / sources with `deg` entries each) cut into segments of `seg` entries: (seg_hub[n], seg_first[h+1])."""
+    d = np.asarray(deg, dtype=np.int64)
+    nseg = (d + seg - 1) // seg
+    first = np.zeros(len(d) + 1, dtype=np.int64)
+    np.cumsum(nseg, out=first[1:])
+    return np.repeat(np.arange(len(d)), nseg), first
+
+
 class RelGraph:
     """E1/E2/E3 edge orders of one adjacency on one CUDA device."""
 
@@ -74,41 +107,18 @@ class RelGraph:
         deg_c = self.colptr[1:] - self.colptr[:-1]
         self.long_rows = torch.nonzero(deg_r > LONG_THRESH).flatten().to(_I32)
         self.long_cols = torch.nonzero(deg_c > LONG_THRESH).flatten().to(_I32)
+        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+
         def segments(deg, hubs):
-            d = deg[hubs.long()].cpu().numpy().astype(np.int64)
-            nseg = (d + LONG_SEG - 1) // LONG_SEG
-            first = np.zeros(len(d) + 1, dtype=np.int64)
-            np.cumsum(nseg, out=first[1:])
-            hub = np.repeat(np.arange(len(d)), nseg)
-            mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+            hub, first = hub_segments(deg[hubs.long()].cpu().numpy(), LONG_SEG)
             return mk(hub if len(hub) else [0]), mk(first), int(first[-1])
         self.row_seg_hub, self.row_seg_first, self.n_row_segs = segments(deg_r, self.long_rows)
         self.col_seg_hub, self.col_seg_first, self.n_col_segs = segments(deg_c, self.long_cols)
-        relptr = self.relptr.cpu().numpy().astype(np.int64)          # groups g = slab*R + rel
         ch = chunk or _chunk_size(self.E)
-        ngrp = len(relptr) - 1
-        cnt = np.diff(relptr)
-        nch = (cnt + ch - 1) // ch
-        grp_chunk_ptr = np.zeros(ngrp + 1, dtype=np.int64)
-        np.cumsum(nch, out=grp_chunk_ptr[1:])
-        n_chunks = int(grp_chunk_ptr[-1])
-        chunk_grp = np.repeat(np.arange(ngrp), nch)
-        within = np.arange(n_chunks) - grp_chunk_ptr[chunk_grp]
-        lo = relptr[chunk_grp] + within * ch
-        chunk_ptr = np.empty(n_chunks + 1, dtype=np.int64)
-        chunk_ptr[:-1] = lo
-        chunk_ptr[-1] = relptr[-1]
-        if n_chunks:     # a chunk ends where the next begins or where its group ends
-            hi = np.minimum(lo + ch, relptr[chunk_grp + 1])
-            assert np.array_equal(hi[:-1], chunk_ptr[1:-1]) and hi[-1] == chunk_ptr[-1]
-        chunk_rel = chunk_grp % self.R
-        # chunks of one relation (scattered over the slabs), in slab order: a fixed reduction order
-        order = np.argsort(chunk_rel, kind="stable")
-        rel_chunk_ptr = np.zeros(self.R + 1, dtype=np.int64)
-        np.cumsum(np.bincount(chunk_rel, minlength=self.R), out=rel_chunk_ptr[1:])
+        chunk_rel, chunk_ptr, rel_chunk_ptr, order = chunk_worklist(self.relptr.cpu().numpy(), self.R, ch)
+        n_chunks = len(chunk_rel)
         self.chunk_size = ch
         self.n_chunks = n_chunks
-        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
         self.chunk_rel = mk(chunk_rel) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
         self.chunk_ptr = mk(chunk_ptr)
         self.rel_chunk_ptr = mk(rel_chunk_ptr)

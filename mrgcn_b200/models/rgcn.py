@@ -21,18 +21,13 @@ class RGCN(nn.Module):
         self.p_dropout = p_dropout
         self.layers = nn.ModuleDict()
         self.activations = nn.ModuleDict()
-        indim, outdim, ltype, f_activation = modules[0]
-        self.layers["layer_0"] = GraphConvolution(indim=indim, outdim=outdim, num_relations=num_relations,
-                                                  num_nodes=num_nodes, num_bases=num_bases,
-                                                  featureless=featureless, input_layer=True, bias=bias)
-        self.activations["layer_0"] = f_activation
-        for i, layer in enumerate(modules[1:], 1):
-            indim, outdim, ltype, f_activation = layer
-            self.layers["layer_" + str(i)] = GraphConvolution(indim=indim, outdim=outdim,
-                                                               num_relations=num_relations, num_nodes=num_nodes,
-                                                               num_bases=num_bases, featureless=False,
-                                                               input_layer=False, bias=bias)
-            self.activations["layer_" + str(i)] = f_activation
+        # layer_0 is the input layer (identity term, optionally featureless); the rest are hidden layers (rgcn.py:25-50)
+        for k, (indim, outdim, _ltype, f_activation) in enumerate(modules):
+            name = "layer_%d" % k
+            self.layers[name] = GraphConvolution(indim=indim, outdim=outdim, num_relations=num_relations,
+                                                 num_nodes=num_nodes, num_bases=num_bases, bias=bias,
+                                                 input_layer=(k == 0), featureless=(featureless and k == 0))
+            self.activations[name] = f_activation
         self.num_layers = len(self.layers)
         if link_prediction:
             # DistMult relation embeddings, one row per relation block (rgcn.py:54-61)

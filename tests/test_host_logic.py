@@ -1,0 +1,84 @@
+"""Host-side logic that needs no GPU: work lists of the relation-major kernels, hub segments, synthetic workloads,
+the algorithmic-bytes model and the JSON contract of bench.py's reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_chunk_worklist_tiles_groups_without_crossing_relations():
+    from mrgcn_b200.graph import chunk_worklist
+    R = 5
+    rng = np.random.default_rng(0)
+    cnt = rng.integers(0, 700, size=3 * R)            # 3 slabs x 5 relations, some groups empty
+    cnt[[2, 7]] = 0
+    grpptr = np.concatenate([[0], np.cumsum(cnt)])
+    rel, ptr, rcp, rci = chunk_worklist(grpptr, R, 128)
+    n = len(rel)
+    assert ptr[0] == 0 and ptr[-1] == grpptr[-1] and np.all(np.diff(ptr) > 0) and np.all(np.diff(ptr) <= 128)
+    grp_of_edge = np.repeat(np.arange(3 * R), cnt)
+    for c in range(n):                                 # one group, hence one relation, per chunk
+        g = grp_of_edge[ptr[c]:ptr[c + 1]]
+        assert np.all(g == g[0]) and g[0] % R == rel[c]
+    assert np.array_equal(np.sort(rci), np.arange(n))
+    for r in range(R):
+        mine = rci[rcp[r]:rcp[r + 1]]
+        assert np.all(rel[mine] == r) and np.all(np.diff(mine) > 0)     # slab order = ascending chunk id
+    assert rcp[-1] == n
+    # degenerate: no edges at all
+    rel0, ptr0, rcp0, rci0 = chunk_worklist(np.zeros(R + 1, dtype=np.int64), R, 128)
+    assert len(rel0) == 0 and list(ptr0) == [0] and rcp0[-1] == 0
+
+
+def test_hub_segments():
+    from mrgcn_b200.graph import hub_segments
+    hub, first = hub_segments([513, 512, 1, 2000], 512)
+    assert list(first) == [0, 2, 3, 4, 8] and list(hub) == [0, 0, 1, 2, 3, 3, 3, 3]
+    hub, first = hub_segments([], 512)
+    assert len(hub) == 0 and list(first) == [0]
+
+
+def test_synthetic_shapes_follow_the_named_configs():
+    from mrgcn_b200.synth import SHAPES, synth_graph
+    am = SHAPES["am"]
+    assert am.num_relations == 267 and am.dims == (151, 10, 11) and am.num_bases == 40 and am.nnz == 13466764
+    n, tr = synth_graph("aifb", seed=0)
+    assert n == 8285 and tr.shape[1] == 3 and tr.dtype == np.int32
+    assert len(np.unique(tr, axis=0)) == len(tr)                       # RDF graphs are sets
+    assert set(np.unique(tr[:, 1])) == set(range(SHAPES["aifb"].num_props))   # every property occurs
+    n2, tr2 = synth_graph("aifb", seed=0)
+    assert np.array_equal(tr, tr2)                                      # seeded
+
+
+def test_algorithmic_bytes_model():
+    sys.path.insert(0, ROOT)
+    import bench
+    g = dict(E=13466744, ND=1666764, NS=1666764, R=267, n_chunks=17000)
+    ab = bench.algorithmic_bytes(g, 151, (10, 11), 40)
+    total = sum(sum(v) for v in ab.values())
+    assert 38e9 < total < 45e9                                          # ~41.6 GB per AM step
+    assert len(ab["feat_msg_fwd"]) == 2 and ab["feat_msg_fwd"][0] > 8e9  # the layer-0 launch gathers E*in*4 bytes
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-scale", "0.002"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
