@@ -163,6 +163,21 @@ class RelGraph:
         return cls.from_coo_arrays(idx[0], idx[1], val, A.shape[0], A.shape[1], R, chunk)
 
     @classmethod
+    def from_csr(cls, A, R, device="cuda", value_dtype=None, chunk=None):
+        """The stacked adjacency as the reference stores it (scipy CSR from the tarball's A.npz: data / indices / indptr,
+        /root/reference/mrgcn/data/io/tarball.py:151-157) straight to the device edge orders, without the detour through
+        `.nonzero()` and an int64 COO tensor on the host.  value_dtype=torch.int8 reproduces the truncation of
+        FullBatch.as_tensors_ (mrgcn/data/batch.py:148-149: 1/deg -> 0 for deg >= 2); default keeps the float values."""
+        device = torch.device(device)
+        indptr = torch.from_numpy(np.asarray(A.indptr, dtype=np.int64)).to(device)
+        col = torch.from_numpy(np.asarray(A.indices, dtype=np.int64)).to(device)
+        val = torch.from_numpy(np.asarray(A.data, dtype=np.float32)).to(device)
+        if value_dtype is not None:
+            val = val.to(value_dtype).float()
+        row = torch.repeat_interleave(torch.arange(A.shape[0], device=device), indptr[1:] - indptr[:-1])
+        return cls.from_coo_arrays(row, col, val, A.shape[0], A.shape[1], R, chunk)
+
+    @classmethod
     def from_triples(cls, triples, num_nodes, num_props, include_inverse=True, device="cuda", chunk=None):
         """Integer triples (s,p,o) -> normalised stacked adjacency built on the GPU, bit-exact with
         mrgcn/encodings/graph_structure.py:70-108,162-169 + the float32 cast of tarball.py:151-157."""

@@ -127,6 +127,22 @@ def test_adjacency_from_triples_bit_exact(golden):
         assert np.array_equal(val[lo:hi].view(np.int32), g["data32"][lo:hi][o].view(np.int32))   # fp32(1/deg) bit-exact
 
 
+def test_graph_from_scipy_csr_matches_coo_hand_off(golden):
+    """RelGraph.from_csr (tarball CSR -> device) gives the same structure as the reference's CSR -> COO hand-off,
+    for float values and for the int8 truncation of FullBatch.as_tensors_ (batch.py:148-149)."""
+    from mrgcn_b200.graph import RelGraph
+    from oracle import reference_port as rp
+    g = golden("adjacency")
+    N, P = int(g["num_nodes"]), int(g["num_props"])
+    R = 2 * P + 1
+    A32 = rp.as_float32(rp.stacked_adjacency(g["triples"], N, P))
+    for dt in (torch.float32, torch.int8):
+        a = RelGraph.from_coo(rp.csr_to_coo(A32, dt), R)
+        b = RelGraph.from_csr(A32, R, value_dtype=None if dt == torch.float32 else dt)
+        for name in ("rowptr", "e1_src", "e1_rel", "e1_val", "colptr", "e2_dst", "e2_rel", "relptr", "e3_src", "e3_dst"):
+            assert torch.equal(getattr(a, name)[:a.E], getattr(b, name)[:b.E]), (dt, name)
+
+
 def test_adjacency_from_triples_vs_oracle_large():
     from mrgcn_b200.graph import RelGraph
     from mrgcn_b200.synth import synth_triples
