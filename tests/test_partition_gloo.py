@@ -74,42 +74,44 @@ def _worker(rank, world, port, tmp):
     try:
         from mrgcn_b200.partition import PartitionedRGCN, balanced_bounds, node_weights
         from mrgcn_b200.synth import synth_triples
-        N, P, B = 200, 3, 2
+        N, P = 200, 3
         R = 2 * P + 1
         A = rp.as_float32(rp.stacked_adjacency(synth_triples(N, P, 1500, seed=4), N, P))
         coo = A.tocoo()
         row, col, val = (torch.from_numpy(np.asarray(a)) for a in (coo.row.astype(np.int64), coo.col.astype(np.int64), coo.data))
-        torch.manual_seed(0)
-        modules = [(5, 6, "mrgcn", nn.ReLU()), (6, 3, "mrgcn", None)]
-        layers, _ = rp.init_rgcn_params(modules, R, N, B, False, True, False)
-        X = torch.randn(N, 5)
-        G = torch.randn(N, 3)
-        # unpartitioned oracle
-        for l in layers:
-            for v in l.values():
-                v.requires_grad_(True)
-        ref = rp.rgcn_forward(layers, ["relu", None], X, rp.csr_to_coo(A, torch.float32), num_nodes=N, num_relations=R,
-                              num_bases=B, featureless=False)
-        (ref * G).sum().backward()
-        # partitioned
         bounds = balanced_bounds(node_weights(row, col, N), world)
-        model = PartitionedRGCN(modules, R, N, B, False, True, False, bounds, rank, layer_fn=_oracle_layer, graph_fn=_coo_graph)
-        model.set_graph(row, col, val)
-        full_state = {"layers.layer_%d.%s" % (k, n): v.detach() for k, l in enumerate(layers) for n, v in l.items()}
-        model.load_full_state(full_state)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        out = model(X)
-        assert out.shape == (hi - lo, 3)
-        assert torch.allclose(out, ref[lo:hi].detach(), rtol=1e-5, atol=1e-6)
-        (out * G[lo:hi]).sum().backward()
-        model.sync_grads()
-        for k, l in enumerate(layers):
-            for n, v in l.items():
-                g = dict(model.named_parameters())["layers.layer_%d.%s" % (k, n)].grad
-                want = v.grad
-                if k == 0 and n == "weight_I":
-                    want = want.view(B, N, -1)[:, lo:hi, :].reshape(B * (hi - lo), -1)
-                assert torch.allclose(g, want, rtol=1e-4, atol=1e-5), (k, n, float((g - want).abs().max()))
+        # (dims, bases, featureless): 2-layer featureful NC, 2-layer featureless NC without bases, 1-layer LP-style encoder
+        for dims, B, fl in (((5, 6, 3), 2, False), ((0, 6, 3), -1, True), ((0, 8), 2, True)):
+            torch.manual_seed(0)
+            modules = [(dims[k], dims[k + 1], "mrgcn", nn.ReLU() if (k + 2 < len(dims) or len(dims) == 2) else None)
+                       for k in range(len(dims) - 1)]
+            acts = ["relu" if m[3] is not None else None for m in modules]
+            layers, _ = rp.init_rgcn_params(modules, R, N, B, fl, True, False)
+            X = None if fl else torch.randn(N, dims[0])
+            G = torch.randn(N, dims[-1])
+            for l in layers:
+                for v in l.values():
+                    v.requires_grad_(True)
+            ref = rp.rgcn_forward(layers, acts, X, rp.csr_to_coo(A, torch.float32), num_nodes=N, num_relations=R,
+                                  num_bases=B, featureless=fl)
+            (ref * G).sum().backward()
+            model = PartitionedRGCN(modules, R, N, B, fl, True, False, bounds, rank, layer_fn=_oracle_layer, graph_fn=_coo_graph)
+            model.set_graph(row, col, val)
+            model.load_full_state({"layers.layer_%d.%s" % (k, n): v.detach() for k, l in enumerate(layers) for n, v in l.items()})
+            out = model(X)
+            assert out.shape == (hi - lo, dims[-1])
+            assert torch.allclose(out, ref[lo:hi].detach(), rtol=1e-5, atol=1e-6), (dims, float((out - ref[lo:hi]).abs().max()))
+            (out * G[lo:hi]).sum().backward()
+            model.sync_grads()
+            S = B if B > 0 else R
+            for k, l in enumerate(layers):
+                for n, v in l.items():
+                    g = dict(model.named_parameters())["layers.layer_%d.%s" % (k, n)].grad
+                    want = v.grad
+                    if k == 0 and n == "weight_I":
+                        want = want.view(S, N, -1)[:, lo:hi, :].reshape(S * (hi - lo), -1)
+                    assert torch.allclose(g, want, rtol=1e-4, atol=1e-5), (dims, k, n, float((g - want).abs().max()))
         open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
