@@ -8,12 +8,14 @@ A step = one full-batch training step of the configured model WITHOUT the optimi
 the labelled nodes, backward to every parameter.  edges = nnz of the stacked adjacency (forward + inverse +
 self-loop blocks).  Prints ONE JSON line (rank 0).
 
-  value    : device-resident throughput (features already in HBM), CUDA events, max over ranks
+  value    : device-resident throughput (features already in HBM), CUDA events, max over ranks; the K timed steps are
+             replays of ONE captured CUDA graph of the step (static in full-batch training); --no-graph times eager launches
   e2e      : the same step through the public module call `MRGCN.forward(batch)` with the feature matrix in
              pinned HOST memory (copied to the device every step, as the reference's forward does,
              mrgcn/models/mrgcn.py:203-204) and the loss read back to the host
-  roofline : dominant kernel of the step, timed live with CUDA events inside the library
-             (mrgcn_profile_enable), against MEASURED_PEAKS.json
+  roofline : dominant kernel of the step, timed live with CUDA events inside the library (mrgcn_profile_enable) in an
+             eager pass of the same K steps, against MEASURED_PEAKS.json; `traffic` = its DRAM bytes per launch from the
+             ncu capture recorded in profiles/ncu_traffic.json
   cpu_baseline / --impl reference : the CPU oracle (the reference's own torch.sparse op sequence,
              oracle/reference_port.py) on a bounded sample of the same workload, on this box's host cores
 
