@@ -327,7 +327,7 @@ int launch_feat_msg_tc(const mrgcn_graph *g, const int32_t *gather, const float 
   static int pieces = 0;
   if (!pieces) {
     const char *e = getenv("MRGCN_FEAT_TC_PIECES");
-    pieces = (e && e[0] == '3') ? 3 : 2;
+    pieces = (e && e[0] == '2') ? 2 : 3;   // three pieces unless MRGCN_FEAT_TC_PIECES=2 (plain 3xTF32) is asked for
   }
   const int NP = out <= 16 ? 16 : 32;
   const int NKC = (int)cdiv(in, 32);

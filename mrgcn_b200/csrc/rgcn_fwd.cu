@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd_v4(AggArgs a) {
   const int rpw = 32 / G;
   const int slot = lane / G, o0 = (lane - slot * G) * 4;
   const int i = gw * rpw + slot;
-  if (i >= a.ND || o0 >= od) return;
+  if (slot >= rpw || i >= a.ND || o0 >= od) return;   // G need not divide 32: the spare lanes must not start the next warp's row
   if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (a.rowptr) {
@@ -674,7 +674,10 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
       if (int rc = launch_feat_msg(gF, gF->e3_src, a->X, W, a->msg_F, in, out, st, "feat_msg_fwd")) return rc;
     g.pF = gF->e1_to_e3; g.msgF = a->msg_F; g.rowptrF = gF->rowptr;
   }
-  // long rows are those of either graph; the host side builds the union list on the owner graph
+  // Long rows are taken from the owner graph (gI when there is an identity term).  The two graphs differ only in
+  // mini-batch mode, where gF is a column slice of gI's adjacency, so a row of gF is never longer than the same row of
+  // gI; a caller that breaks this (E_F > E_I) is refused instead of leaving hub rows unwritten.
+  MRGCN_REQUIRE(!(hasI && hasF) || gF->E <= gI->E, MRGCN_E_BADARG, "layer_fwd: feature graph has more entries than the identity graph");
   g.thresh = gl->n_long_rows > 0 ? gl->long_row_thresh : 0;
   HubSegs hs{gl->long_rows, gl->row_seg_hub, gl->row_seg_first, gl->n_long_rows, gl->n_row_segs, gl->long_seg, a->hub_ws};
   if (int rc = launch_agg(g, hs, st, "agg_fwd")) return rc;

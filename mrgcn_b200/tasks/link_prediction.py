@@ -90,10 +90,15 @@ def _filter_csr(data, true_dict, head):
     return np.asarray(ptr, dtype=np.int32), np.asarray(idx if idx else [0], dtype=np.int32)
 
 
+RANK_WS_BYTES = 2 << 30      # score workspace per ranking call; larger fact sets are processed in chunks
+
+
 def compute_ranks_fast(data, node_embeddings, edge_embeddings, batch_size=16, filtered=True):
     """Ranks of every fact against all N candidate tails, then all candidate heads (loop order of
-    link_prediction.py:602).  `batch_size` (the reference's mrr_batchsize chunking, :618-625) is accepted
-    and ignored: one fused pass scores every candidate.  Returns int64 (2*facts,), 1-based."""
+    link_prediction.py:602).  `batch_size` (the reference's mrr_batchsize chunking of the fact axis, :618-625) does not
+    change any result and is not needed for memory here: facts are processed in chunks sized to a fixed workspace
+    (and to the 65 535-facts-per-call limit of the C entry point).  The filter dictionaries are built over ALL facts of
+    `data`, as the reference does (:597-600).  Returns int64 (2*facts,), 1-based."""
     E = node_embeddings.detach().float().contiguous()
     nv.require_cuda(E, "node_embeddings")
     dev = E.device
@@ -101,16 +106,20 @@ def compute_ranks_fast(data, node_embeddings, edge_embeddings, batch_size=16, fi
     data_h = torch.as_tensor(data).cpu().long()
     facts = data_h.to(dev).contiguous()
     F, N, h = facts.shape[0], E.shape[0], E.shape[1]
-    true_heads, true_tails = truedicts(data_h.numpy()) if filtered else (None, None)
+    data_np = data_h.numpy()
+    true_heads, true_tails = truedicts(data_np) if filtered else (None, None)
     out = torch.empty(2 * F, dtype=torch.int64, device=dev)
-    ws = torch.empty(max(F * N, 1), dtype=torch.float32, device=dev)
+    chunk = int(max(1, min(65535, RANK_WS_BYTES // (4 * N), F)))
+    ws = torch.empty(max(chunk * N, 1), dtype=torch.float32, device=dev)
     for k, head in enumerate((False, True)):
-        fptr = fidx = None
-        if filtered:
-            p_, i_ = _filter_csr(data_h.numpy(), true_heads if head else true_tails, head)
-            fptr, fidx = torch.from_numpy(p_).to(dev), torch.from_numpy(i_).to(dev)
-        with torch.cuda.device(dev):
-            nv.check(nv.lib().mrgcn_distmult_rank(nv.ptr(facts), F, int(head), nv.ptr(E), nv.ptr(Rel), N, h,
-                                                  nv.ptr(fptr), nv.ptr(fidx), nv.ptr(ws), nv.ptr(out[k * F:]),
-                                                  nv.stream_ptr()), "distmult_rank")
+        for f0 in range(0, F, chunk):
+            f1 = min(F, f0 + chunk)
+            fptr = fidx = None
+            if filtered:
+                p_, i_ = _filter_csr(data_np[f0:f1], true_heads if head else true_tails, head)
+                fptr, fidx = torch.from_numpy(p_).to(dev), torch.from_numpy(i_).to(dev)
+            with torch.cuda.device(dev):
+                nv.check(nv.lib().mrgcn_distmult_rank(nv.ptr(facts[f0:f1]), f1 - f0, int(head), nv.ptr(E), nv.ptr(Rel), N, h,
+                                                      nv.ptr(fptr), nv.ptr(fidx), nv.ptr(ws), nv.ptr(out[k * F + f0:]),
+                                                      nv.stream_ptr()), "distmult_rank")
     return out

@@ -140,8 +140,11 @@ def init_rgcn_params(modules, num_relations, num_nodes, num_bases, featureless, 
 # the layer  (mrgcn/layers/graph.py:62-102)
 # --------------------------------------------------------------------------------------
 def graphconv_forward(p, X, A, *, num_nodes, num_relations, num_bases, input_layer, featureless,
-                      A_idx=None):
-    """One R-GCN layer, same op sequence as GraphConvolution.forward."""
+                      A_idx=None, dtype=torch.float32):
+    """One R-GCN layer, same op sequence as GraphConvolution.forward.
+    dtype: torch.float32 is the reference (`A.float()`, graph.py:75,95); torch.float64 with double parameters / X
+    evaluates the same op sequence in double precision — the "truth" the parity tests adjudicate fp32 rounding
+    differences against (tests/parity.py)."""
     outdim = (p["weight_I"] if "weight_I" in p else p["weight_F"]).shape[-1]
     ident = 0.0
     if input_layer:
@@ -150,7 +153,7 @@ def graphconv_forward(p, X, A, *, num_nodes, num_relations, num_bases, input_lay
             W_I = torch.einsum("rb,bij->rij", p["weight_I_comp"],
                                W_I.view(num_bases, num_nodes, outdim))
             W_I = W_I.view(num_relations * num_nodes, outdim)
-        ident = torch.mm(A.float(), W_I)                                    # graph.py:75
+        ident = torch.mm(A.to(dtype), W_I)                                    # graph.py:75
         if featureless:                                                     # graph.py:77-81
             return ident + p["b"] if "b" in p else ident
     W_F = p["weight_F"]
@@ -161,7 +164,7 @@ def graphconv_forward(p, X, A, *, num_nodes, num_relations, num_bases, input_lay
         n = X.shape[0]
         A = slice_columns(A, A_idx)
     proj = torch.einsum("ij,bjk->bik", X, W_F).reshape(num_relations * n, outdim)   # :93-94
-    feat = torch.mm(A.float(), proj)                                        # graph.py:95
+    feat = torch.mm(A.to(dtype), proj)                                        # graph.py:95
     out = ident + feat if input_layer else feat                             # graph.py:97
     if "b" in p:
         out = out + p["b"]                                                  # graph.py:99-100
@@ -169,13 +172,13 @@ def graphconv_forward(p, X, A, *, num_nodes, num_relations, num_bases, input_lay
 
 
 def rgcn_forward(layers, activations, X, A, *, num_nodes, num_relations, num_bases, featureless,
-                 row_masks=None):
+                 row_masks=None, dtype=torch.float32):
     """rgcn.py:69-89, full batch.  `row_masks[k]` (shape (N,), already scaled by 1/(1-p)) stands
     in for the dropout-on-ones vector of rgcn.py:82-84, whose RNG stream is not reproducible."""
     for k, (p, act) in enumerate(zip(layers, activations)):
         X = graphconv_forward(p, X, A, num_nodes=num_nodes, num_relations=num_relations,
                               num_bases=num_bases, input_layer=(k == 0),
-                              featureless=(featureless if k == 0 else False))
+                              featureless=(featureless if k == 0 else False), dtype=dtype)
         if row_masks is not None and row_masks[k] is not None:
             X = torch.mul(X.T, row_masks[k]).T
         if act == "relu":
@@ -194,13 +197,13 @@ def mlp_forward(weights, x):
     return x
 
 
-def modality_features(num_nodes, sets, gate_weights):
+def modality_features(num_nodes, sets, gate_weights, dtype=torch.float32):
     """mrgcn.py:250-305 for a full batch: zeros (N, sum dim); per encoding set (in order) the encoder output times its
     gate weight is written into the rows listed in node_idx.  sets: [(mlp_weights, encodings, node_idx), ...]."""
     cols = []
     for i, (weights, enc, node_idx) in enumerate(sets):
-        out = mlp_forward(weights, enc.float()) * gate_weights[i]
-        block = torch.zeros((num_nodes, out.shape[1]), dtype=torch.float32)
+        out = mlp_forward(weights, enc.to(dtype)) * gate_weights[i]
+        block = torch.zeros((num_nodes, out.shape[1]), dtype=dtype)
         block = block.index_put((torch.as_tensor(node_idx),), out)
         cols.append(block)
     return torch.cat(cols, dim=1)
