@@ -93,6 +93,30 @@ typedef struct mrgcn_graph {
   int32_t n_chunks, slab_rows; /* slab_rows: input of mrgcn_graph_build (0 = one slab) */
 } mrgcn_graph;
 
+/* Work plan of the table-term kernels (tab.cu) over the source-major order E2 of one graph; built by the host side
+ * (mrgcn_b200/graph.py: RelGraph.tab_plan) from colptr / e2_rel, once per graph.
+ *   task          up to `lt` consecutive E2 edges of one source (a source with more edges has several tasks)
+ *   wsrc          the sources with at most long_col_thresh edges, ordered by degree inside windows of 192 sources
+ *   tile          consecutive tasks covering at most `tile_slots` E2 edges, one CTA at a time
+ *   piece         at most 32 edges of ONE relation inside one tile; tperm lists the tile-local edge slots of every tile
+ *                 in (relation, E2 position) order, piece_ptr cuts that list into pieces; the comp gradient of relation
+ *                 r is the sum, in rel_piece_idx order, of the records of its pieces. */
+typedef struct mrgcn_tab_plan {
+  int32_t n_tasks, n_wsrc, n_tiles, n_pieces, tile_slots, lt, _pad0, _pad1;
+  int32_t *task_src, *task_lo;   /* [n_tasks] source and first E2 edge of task t */
+  int32_t *wsrc;                 /* [n_wsrc] */
+  int32_t *tile_task_ptr;        /* [n_tiles+1] */
+  int32_t *tile_e0;              /* [n_tiles] first E2 edge of the tile */
+  int32_t *tperm;                /* [E] */
+  int32_t *piece_ptr;            /* [n_pieces+1] positions in tperm */
+  int32_t *tile_piece_ptr;       /* [n_tiles+1] */
+  int32_t *rel_piece_ptr;        /* [R+1] */
+  int32_t *rel_piece_idx;        /* [n_pieces] */
+} mrgcn_tab_plan;
+/* which table-term kernels apply to (B_I identity bases, B_F projected feature bases, out): bit 0 forward messages,
+ * bit 1 basis gradient, bit 2 comp gradient without the E x B scratch (cbuf then holds n_pieces x B records). */
+int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out);
+
 /* Re-emit the reference's stacked adjacency as E1/E2/E3.
  * Replaces: scipy CSR -> torch COO hand-off (mrgcn/data/utils.py:165-170, mrgcn/data/batch.py:144-149)
  * and the per-call coalesce/sort inside torch.mm(sparse, dense) (mrgcn/layers/graph.py:75,95).
@@ -139,6 +163,13 @@ typedef struct mrgcn_layer_args {
   float *wmix, *msg_I, *msg_F;
   float *hub_ws; /* [max(n_row_segs, n_col_segs) * max(out, in, B*out)] partial sums of hub segments (may be NULL without hubs) */
   float *out; /* [ND, out] */
+  /* table-term kernels (tab.cu): plan of gI (NULL = the tile-staging kernels of round 1);
+   * proj [NS, B, out] workspace: per-basis projection of the features, X . weight_F[b] (feat_proj.cu) - when given
+   * (and the shape fits, mrgcn_tab_mode bit 0 with B_F = B) the feature term of the input layer is mixed together with the
+   * identity term and msg_F is not used; x_stride: row pitch of X in floats (0 = in_dim). */
+  const mrgcn_tab_plan *plan;
+  float *proj;
+  int32_t x_stride, _pad;
 } mrgcn_layer_args;
 int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);
 
@@ -147,7 +178,8 @@ int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);
  * Gradients are written (not accumulated); NULL pointer = not wanted.
  *   g_weight_I [S*NS_I,out]  g_comp_I [R,B]  g_weight_F [S,in,out]  g_comp_F [R,B]  g_bias [out]
  *   g_X [NS_F,in]
- * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term);
+ * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term; [n_pieces*B] when f.plan is given and
+ *   mrgcn_tab_mode(B, 0, out) has bit 2);
  *   part [n_chunks * max(B, in*out)] ; g_wmix [R*in*out] (B>0 and feature term);
  *   colsum_ws [ceil(ND/1024) * out]; wt_ws, msgx_ws when g_X is wanted. */
 typedef struct mrgcn_layer_bwd_args {

@@ -37,6 +37,17 @@ class Graph(C.Structure):
     ]
 
 
+class TabPlan(C.Structure):
+    """struct mrgcn_tab_plan."""
+    _fields_ = [
+        ("n_tasks", C.c_int32), ("n_wsrc", C.c_int32), ("n_tiles", C.c_int32), ("n_pieces", C.c_int32),
+        ("tile_slots", C.c_int32), ("lt", C.c_int32), ("_pad0", C.c_int32), ("_pad1", C.c_int32),
+        ("task_src", C.c_void_p), ("task_lo", C.c_void_p), ("wsrc", C.c_void_p), ("tile_task_ptr", C.c_void_p),
+        ("tile_e0", C.c_void_p), ("tperm", C.c_void_p), ("piece_ptr", C.c_void_p), ("tile_piece_ptr", C.c_void_p),
+        ("rel_piece_ptr", C.c_void_p), ("rel_piece_idx", C.c_void_p),
+    ]
+
+
 class LayerArgs(C.Structure):
     """struct mrgcn_layer_args."""
     _fields_ = [
@@ -46,6 +57,7 @@ class LayerArgs(C.Structure):
         ("comp_F", C.c_void_p), ("bias", C.c_void_p), ("row_mask", C.c_void_p), ("addend", C.c_void_p),
         ("wmix", C.c_void_p), ("msg_I", C.c_void_p), ("msg_F", C.c_void_p), ("hub_ws", C.c_void_p),
         ("out", C.c_void_p),
+        ("plan", C.POINTER(TabPlan)), ("proj", C.c_void_p), ("x_stride", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -73,6 +85,7 @@ SYMBOLS = {
     "mrgcn_adjacency_from_triples": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrgcn_msg_stride": (C.c_int32, [C.c_int32]),
+    "mrgcn_tab_mode": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgcn_rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), C.c_void_p]),
     "mrgcn_rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), C.c_void_p]),
     "mrgcn_distmult_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,

@@ -684,8 +684,12 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
     } else {
       const int OC = pick_oc(out);
       const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
+      TabGeom tg;
+      const bool tab_w = f.plan && tab_geometry(B, out, tg);
       {  // basis gradient
-        if (B <= 64 && out <= 256) {
+        if (tab_w) {
+          if (int rc = launch_tab_bwd_w(gI, f.plan, f.comp_I, B, out, a->gact, a->g_weight_I, st)) return rc;
+        } else if (B <= 64 && out <= 256) {
           const int BT = (int)cdiv(B, 8) * 8;
           const int TJ = 256 / out;
           const int EC = pick_ec(out);
@@ -741,6 +745,18 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       }
       if (a->g_comp_I) {
         MRGCN_REQUIRE(a->cbuf && a->part, MRGCN_E_BADARG, "layer_bwd: cbuf/part missing");
+        int tBC = 0, tOP = 0;
+        const bool tab_c = f.plan && tab_c_geometry(B, out, tBC, tOP);
+        if (tab_c) {
+          // records of the (tile, relation) pieces, then the fixed-order sum per relation
+          if (gI->E > 0)
+            if (int rc = launch_tab_bwd_c(gI, f.plan, f.weight_I, B, out, a->gact, a->cbuf, st)) return rc;
+          MRGCN_PROF("comp_reduce");
+          k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)gI->R), 256, 0, st>>>(a->cbuf, f.plan->rel_piece_ptr,
+                                                                                      f.plan->rel_piece_idx, f.plan->n_pieces, B,
+                                                                                      a->g_comp_I);
+          MRGCN_LAUNCH_CHECK();
+        } else {
         if (gI->E > 0) {
           unsigned grid = 0;
           size_t smem = 0;
@@ -802,6 +818,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
                                                                                     gI->rel_chunk_idx, gI->n_chunks, B,
                                                                                     a->g_comp_I);
         MRGCN_LAUNCH_CHECK();
+        }
       }
     }
   }

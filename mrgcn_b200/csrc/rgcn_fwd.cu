@@ -655,8 +655,14 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
     g.rowptr = gI->rowptr;
     if (B > 0) {
       MRGCN_REQUIRE(a->comp_I && a->msg_I, MRGCN_E_BADARG, "layer_fwd: comp_I/msg_I missing");
-      if (gI->E > 0)
-        if (int rc = launch_ident_msg_fwd(gI, a->weight_I, a->comp_I, a->msg_I, B, out, st)) return rc;
+      TabGeom tg;
+      if (gI->E > 0) {
+        if (a->plan && tab_geometry(B, out, tg)) {
+          if (int rc = launch_tab_msg_fwd(gI, a->plan, a->weight_I, a->comp_I, B, nullptr, nullptr, 0, out, a->msg_I, st)) return rc;
+        } else {
+          if (int rc = launch_ident_msg_fwd(gI, a->weight_I, a->comp_I, a->msg_I, B, out, st)) return rc;
+        }
+      }
       g.pI = gI->e1_to_e2; g.msgI = a->msg_I;
     } else {
       g.Wd = a->weight_I; g.d_src = gI->e1_src; g.d_rel = gI->e1_rel; g.d_val = gI->e1_val; g.NSd = gI->NS;

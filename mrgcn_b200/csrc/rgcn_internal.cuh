@@ -59,6 +59,16 @@ int launch_agg(const AggArgs &a, const HubSegs &h, cudaStream_t st, const char *
 // tensor-core (tcgen05, 3xTF32) variant of launch_feat_msg; *launched = 0 when it does not apply
 int launch_feat_msg_tc(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
                        int out, cudaStream_t st, const char *prof_name, int *launched);
+// table-term kernels (tab.cu)
+struct TabGeom { int GS, HS, BPT, NOP, CSP; };
+bool tab_geometry(int Btot, int out, TabGeom &g);
+bool tab_c_geometry(int BI, int out, int &BC, int &OP);
+int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, const float *compI, int BI,
+                       const float *TP, const float *compF, int BF, int out, float *msg, cudaStream_t st);
+int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *compI, int BI, int out,
+                     const float *gact, float *gW, cudaStream_t st);
+int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, int BI, int out, const float *gact,
+                     float *rec, cudaStream_t st);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
 struct IdentPipe;

@@ -1,0 +1,525 @@
+// Table term of an input layer with basis decomposition (identity term of /root/reference/mrgcn/layers/graph.py:67-75
+// and, when the features were projected per basis first, the feature term of graph.py:83-95 re-associated):
+//
+//   msg[e, :] = val_e * ( sum_b comp_I[r_e, b] * T_I[b, j_e, :]  +  sum_b comp_F[r_e, b] * T_P[j_e, b, :] )
+//
+// T_I = weight_I in the reference layout [B_I][NS][out] (basis-major); T_P[j, b, :] = X[j, :] . V_F[b] is the per-basis
+// projection of the features (feat_proj.cu, node-major [NS][B_F][out]).  Both tables are indexed by the SOURCE node, so all
+// three passes walk the source-major edge order E2 and keep the table rows of a source in REGISTERS:
+//
+//   tab_msg_fwd : a group of lanes owns (task, output pair[, half of the bases]); a task is up to 32 consecutive E2 edges of
+//                 one source.  The group loads the source's table rows once (coalesced: the lanes of a group cover the
+//                 contiguous `out` floats of a row, consecutive sources are consecutive groups) and then produces one
+//                 message per edge from comp rows read out of shared memory (16-byte loads, broadcast inside the group).
+//   tab_bwd_w   : same ownership, one task per (non-hub) source; accumulates g_T_I[b, j, :] = sum_e comp_I[r_e, b] t_e in
+//                 registers, t_e = val_e * gact[dst_e, :] gathered straight from global memory, four edges in flight.
+//   tab_bwd_c   : a lane owns (task, chunk of bases) and all outputs: c_e[b] = <T_I[b, j_e, :], t_e> goes to a shared-memory
+//                 tile (<= 543 edges x B), which the CTA then sums per relation in a precomputed tile-local relation order
+//                 (pieces of <= 32 edges) -> one record per piece; g_comp_I[r, :] = fixed-order sum of the records of r.
+//                 Nothing of size E x B touches HBM.
+// The reference layout of weight_I makes a per-edge gather of its B rows hostile (B separate 4*out-byte segments N*out*4
+// bytes apart); here every table row is read from HBM exactly once per pass, straight into registers: no shared-memory
+// traffic for the table at all (the round-1 kernels were bound by the shared-memory pipe: one 8-byte read per 2 FMAs).
+// All reductions have a fixed order: bit-reproducible, no float atomics.
+#include "common.cuh"
+#include "rgcn_internal.cuh"
+
+namespace mrgcn {
+namespace {
+
+constexpr int kTabThreads = 256;
+constexpr int kTabWarps = kTabThreads / 32;
+constexpr int LT = 32;  // edges per task (mrgcn_tab_plan.lt)
+
+struct TabTables {
+  const float *TI;  // [BI][NS][out] or NULL
+  const float *TP;  // [NS][BF][out] or NULL
+  int BI, BF, out;
+  int64_t NS;
+};
+
+__device__ __forceinline__ const float *tab_row(const TabTables &t, int bb, int64_t j) {
+  return bb < t.BI ? t.TI + ((size_t)bb * t.NS + j) * t.out : t.TP + ((size_t)j * t.BF + (bb - t.BI)) * t.out;
+}
+__device__ __forceinline__ float2 ld_pair(const float *p, int o, int out, bool even) {
+  if (even) return *reinterpret_cast<const float2 *>(p + o);
+  return make_float2(p[o], o + 1 < out ? p[o + 1] : 0.f);
+}
+__device__ __forceinline__ void st_pair(float *p, int o, int out, bool even, float2 v) {
+  if (even) { *reinterpret_cast<float2 *>(p + o) = v; return; }
+  p[o] = v.x;
+  if (o + 1 < out) p[o + 1] = v.y;
+}
+
+// lane geometry shared by the kernels that own (task, output pair, base split)
+struct Geo {
+  int LPT, TPW, tslot, hs, op0;
+  bool lane_on;
+  __device__ Geo(int GS, int HS, int lane) {
+    LPT = GS > 32 ? 32 : GS * HS;
+    TPW = 32 / LPT;
+    tslot = lane / LPT;
+    const int within = lane - tslot * LPT;
+    hs = GS > 32 ? 0 : within / GS;
+    op0 = GS > 32 ? within : within - hs * GS;
+    lane_on = tslot < TPW;
+  }
+};
+
+__device__ __forceinline__ void fill_comp(float *comp_s, const float *__restrict__ compI, const float *__restrict__ compF,
+                                          int R, int BI, int BF, int CSP) {
+  for (int x = threadIdx.x; x < R * CSP; x += kTabThreads) {
+    const int r = x / CSP, bb = x - r * CSP;
+    float c = 0.f;
+    if (bb < BI) c = __ldg(compI + (size_t)r * BI + bb);
+    else if (bb < BI + BF) c = __ldg(compF + (size_t)r * BF + (bb - BI));
+    comp_s[x] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int BPT, int NOP>
+__global__ void __launch_bounds__(kTabThreads, 2)
+k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__restrict__ compF, int R,
+              const int32_t *__restrict__ colptr, const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
+              int n_tasks, const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, float *__restrict__ msg,
+              int ms, int GS, int HS, int CSP) {
+  extern __shared__ __align__(16) float smem[];
+  float *comp_s = smem;                                             // [R][CSP]
+  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)R * CSP);    // [warps][TPW*LT] (rel, val)
+  fill_comp(comp_s, compI, compF, R, tb.BI, tb.BF, CSP);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Geo g(GS, HS, lane);
+  const int Btot = tb.BI + tb.BF, out = tb.out;
+  const bool even = (out & 1) == 0;
+  int2 *wmeta = meta + (size_t)warp * g.TPW * LT;
+  const int n_items = (n_tasks + g.TPW - 1) / g.TPW;
+  for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
+    __syncwarp();
+    for (int ts = 0; ts < g.TPW; ++ts) {
+      const int t = wi * g.TPW + ts;
+      if (t < n_tasks) {
+        const int j = task_src[t], lo = task_lo[t];
+        const int len = min(LT, colptr[j + 1] - lo);
+        if (lane < len) wmeta[ts * LT + lane] = make_int2(ldg_stream(e2_rel + lo + lane), __float_as_int(ldg_stream(e2_val + lo + lane)));
+      }
+    }
+    const int t = wi * g.TPW + g.tslot;
+    const bool on = g.lane_on && t < n_tasks;
+    int j = 0, lo = 0, len = 0;
+    if (on) { j = task_src[t]; lo = task_lo[t]; len = min(LT, colptr[j + 1] - lo); }
+    float2 T[BPT][NOP];
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      const int bb = g.hs * BPT + b;
+      const float *row = (on && bb < Btot) ? tab_row(tb, bb, j) : nullptr;
+#pragma unroll
+      for (int q = 0; q < NOP; ++q) {
+        const int o = 2 * (g.op0 + 32 * q);
+        T[b][q] = (row && o < out) ? ld_pair(row, o, out, even) : make_float2(0.f, 0.f);
+      }
+    }
+    __syncwarp();
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    for (int s = 0; s < maxlen; ++s) {
+      const bool live = s < len;
+      const int2 m = live ? wmeta[g.tslot * LT + s] : make_int2(0, 0);
+      const float *cr = comp_s + (size_t)m.x * CSP + g.hs * BPT;
+      float2 acc[NOP], acc1[NOP];   // two chains per output pair (even / odd groups of four bases), added at the end
+#pragma unroll
+      for (int q = 0; q < NOP; ++q) { acc[q] = make_float2(0.f, 0.f); acc1[q] = make_float2(0.f, 0.f); }
+#pragma unroll
+      for (int b = 0; b < BPT; b += 4) {
+        const float4 c = *reinterpret_cast<const float4 *>(cr + b);
+#pragma unroll
+        for (int q = 0; q < NOP; ++q) {
+          float2 &a = ((b >> 2) & 1) ? acc1[q] : acc[q];
+          fma2(a, c.x, T[b][q]);
+          fma2(a, c.y, T[b + 1][q]);
+          fma2(a, c.z, T[b + 2][q]);
+          fma2(a, c.w, T[b + 3][q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NOP; ++q) { acc[q].x += acc1[q].x; acc[q].y += acc1[q].y; }
+      if (HS > 1) {   // partial sums of the base splits, added in split order
+#pragma unroll
+        for (int q = 0; q < NOP; ++q) {
+          const float2 own = acc[q];
+          for (int h = 1; h < HS; ++h) {
+            acc[q].x += __shfl_down_sync(0xffffffffu, own.x, h * GS);
+            acc[q].y += __shfl_down_sync(0xffffffffu, own.y, h * GS);
+          }
+        }
+      }
+      if (live && g.hs == 0) {
+        const float v = __int_as_float(m.y);
+        float *row = msg + (size_t)(lo + s) * ms;
+#pragma unroll
+        for (int q = 0; q < NOP; ++q) {
+          const int op = g.op0 + 32 * q, o = 2 * op;
+          if (o < out) {
+            // rows are padded to `ms` floats (even, >= out): the pad is written as zeros
+            *reinterpret_cast<float2 *>(row + o) = make_float2(v * acc[q].x, o + 1 < out ? v * acc[q].y : 0.f);
+            if (op == GS - 1)
+              for (int z = 2 * GS; z < ms; z += 2) *reinterpret_cast<float2 *>(row + z) = make_float2(0.f, 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct __align__(16) EdgeMeta { int d, r; float v; int pad; };
+
+template <int BPT, int NOP>
+__global__ void __launch_bounds__(kTabThreads, (BPT * NOP >= 24) ? 1 : 2)
+k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
+            const int32_t *__restrict__ wsrc, int n_src, const int32_t *__restrict__ e2_dst,
+            const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
+            float *__restrict__ gW, int GS, int HS, int CSP) {
+  extern __shared__ __align__(16) float smem[];
+  float *comp_s = smem;                                                     // [R][CSP]
+  EdgeMeta *meta = reinterpret_cast<EdgeMeta *>(smem + (size_t)R * CSP);    // [warps][TPW*32]
+  fill_comp(comp_s, compI, nullptr, R, BI, 0, CSP);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Geo g(GS, HS, lane);
+  const bool even = (out & 1) == 0;
+  EdgeMeta *wmeta = meta + (size_t)warp * g.TPW * 32;
+  const int n_items = (n_src + g.TPW - 1) / g.TPW;
+  for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
+    const int t = wi * g.TPW + g.tslot;
+    const bool on = g.lane_on && t < n_src;
+    int j = 0, e_lo = 0, len = 0;
+    if (on) { j = wsrc[t]; e_lo = colptr[j]; len = colptr[j + 1] - e_lo; }
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    float2 acc[BPT][NOP];
+#pragma unroll
+    for (int b = 0; b < BPT; ++b)
+#pragma unroll
+      for (int q = 0; q < NOP; ++q) acc[b][q] = make_float2(0.f, 0.f);
+    for (int c0 = 0; c0 < maxlen; c0 += 32) {
+      __syncwarp();
+      for (int ts = 0; ts < g.TPW; ++ts) {
+        const int src_lane = ts * g.LPT;
+        const int lo_ts = __shfl_sync(0xffffffffu, e_lo, src_lane), len_ts = __shfl_sync(0xffffffffu, len, src_lane);
+        if (lane < len_ts - c0) {
+          const int e = lo_ts + c0 + lane;
+          EdgeMeta m;
+          m.d = ldg_stream(e2_dst + e); m.r = ldg_stream(e2_rel + e); m.v = ldg_stream(e2_val + e); m.pad = 0;
+          wmeta[ts * 32 + lane] = m;
+        }
+      }
+      __syncwarp();
+      const int nch = min(32, maxlen - c0);
+      const int mylen = min(32, max(0, len - c0));
+      for (int s0 = 0; s0 < nch; s0 += 4) {
+        EdgeMeta m[4];
+        float2 t[4][NOP];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool live = s0 + u < mylen;
+          if (live) m[u] = wmeta[g.tslot * 32 + s0 + u];
+          else { m[u].d = 0; m[u].r = 0; m[u].v = 0.f; }
+#pragma unroll
+          for (int q = 0; q < NOP; ++q) {
+            const int o = 2 * (g.op0 + 32 * q);
+            t[u][q] = (live && o < out) ? ld_pair(gact + (size_t)m[u].d * out, o, out, even) : make_float2(0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float *cr = comp_s + (size_t)m[u].r * CSP + g.hs * BPT;
+#pragma unroll
+          for (int q = 0; q < NOP; ++q) { t[u][q].x *= m[u].v; t[u][q].y *= m[u].v; }
+#pragma unroll
+          for (int b = 0; b < BPT; b += 4) {
+            const float4 c = *reinterpret_cast<const float4 *>(cr + b);
+#pragma unroll
+            for (int q = 0; q < NOP; ++q) {
+              fma2(acc[b][q], c.x, t[u][q]);
+              fma2(acc[b + 1][q], c.y, t[u][q]);
+              fma2(acc[b + 2][q], c.z, t[u][q]);
+              fma2(acc[b + 3][q], c.w, t[u][q]);
+            }
+          }
+        }
+      }
+    }
+    if (on) {
+#pragma unroll
+      for (int b = 0; b < BPT; ++b) {
+        const int bb = g.hs * BPT + b;
+        if (bb < BI) {
+          float *row = gW + ((size_t)bb * NS + j) * out;
+#pragma unroll
+          for (int q = 0; q < NOP; ++q) {
+            const int o = 2 * (g.op0 + 32 * q);
+            if (o < out) st_pair(row, o, out, even, acc[b][q]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int BC, int OP>
+__global__ void __launch_bounds__(kTabThreads, 2)
+k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
+            const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
+            const int32_t *__restrict__ tile_task_ptr, const int32_t *__restrict__ tile_e0, int n_tiles,
+            const int32_t *__restrict__ e2_dst, const float *__restrict__ e2_val, const float *__restrict__ gact,
+            const int32_t *__restrict__ tperm, const int32_t *__restrict__ piece_ptr,
+            const int32_t *__restrict__ tile_piece_ptr, float *__restrict__ rec, int LPT, int BSP, int tile_slots) {
+  extern __shared__ __align__(16) float smem[];
+  float *Cs = smem;                                                       // [tile_slots][BSP]
+  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)tile_slots * BSP); // [warps][TPW*LT] (dst, val)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int TPW = 32 / LPT;
+  const int tslot = lane / LPT, gch = lane - tslot * LPT;   // base chunk of this lane
+  const bool lane_on = tslot < TPW;
+  const bool even = (out & 1) == 0;
+  int2 *wmeta = meta + (size_t)warp * TPW * LT;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int e0 = tile_e0[tile], t_lo = tile_task_ptr[tile], t_hi = tile_task_ptr[tile + 1];
+    const int n_items = (t_hi - t_lo + TPW - 1) / TPW;
+    for (int wi = warp; wi < n_items; wi += kTabWarps) {
+      __syncwarp();
+      for (int ts = 0; ts < TPW; ++ts) {
+        const int t = t_lo + wi * TPW + ts;
+        if (t < t_hi) {
+          const int j = task_src[t], lo = task_lo[t];
+          const int len = min(LT, colptr[j + 1] - lo);
+          if (lane < len) wmeta[ts * LT + lane] = make_int2(ldg_stream(e2_dst + lo + lane), __float_as_int(ldg_stream(e2_val + lo + lane)));
+        }
+      }
+      const int t = t_lo + wi * TPW + tslot;
+      const bool on = lane_on && t < t_hi;
+      int j = 0, lo = 0, len = 0;
+      if (on) { j = task_src[t]; lo = task_lo[t]; len = min(LT, colptr[j + 1] - lo); }
+      float2 T[BC][OP];
+#pragma unroll
+      for (int b = 0; b < BC; ++b) {
+        const int bb = gch * BC + b;
+        const float *row = (on && bb < BI) ? TI + ((size_t)bb * NS + j) * out : nullptr;
+#pragma unroll
+        for (int q = 0; q < OP; ++q) T[b][q] = (row && 2 * q < out) ? ld_pair(row, 2 * q, out, even) : make_float2(0.f, 0.f);
+      }
+      __syncwarp();
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      for (int s = 0; s < maxlen; ++s) {
+        const bool live = s < len;
+        const int2 m = live ? wmeta[tslot * LT + s] : make_int2(0, 0);
+        const float v = __int_as_float(m.y);
+        const float *gp = gact + (size_t)m.x * out;
+        float2 tv[OP];
+#pragma unroll
+        for (int q = 0; q < OP; ++q) {
+          tv[q] = (live && 2 * q < out) ? ld_pair(gp, 2 * q, out, even) : make_float2(0.f, 0.f);
+          tv[q].x *= v; tv[q].y *= v;
+        }
+        if (live) {
+          float *crow = Cs + (size_t)(lo + s - e0) * BSP + gch * BC;
+#pragma unroll
+          for (int b = 0; b < BC; b += 4) {
+            float c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < OP; ++q) fma2v(a2, T[b + u][q], tv[q]);
+              c[u] = a2.x + a2.y;
+            }
+            *reinterpret_cast<float4 *>(crow + b) = make_float4(c[0], c[1], c[2], c[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // per-relation pieces of the tile, summed in the precomputed order
+    const int p_lo = tile_piece_ptr[tile], p_hi = tile_piece_ptr[tile + 1];
+    for (int x = threadIdx.x; x < (p_hi - p_lo) * BI; x += kTabThreads) {
+      const int pc = p_lo + x / BI, b = x - (pc - p_lo) * BI;
+      const int q_lo = piece_ptr[pc], q_hi = piece_ptr[pc + 1];
+      float acc = 0.f;
+      for (int q = q_lo; q < q_hi; ++q) acc += Cs[(size_t)tperm[q] * BSP + b];
+      rec[(size_t)pc * BI + b] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+template <class K>
+static int tab_set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) MRGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+template <class K>
+static unsigned tab_grid(K kernel, size_t smem, int64_t max_ctas) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTabThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t g = (int64_t)kNumSMs * per_sm;
+  return (unsigned)(g < max_ctas ? g : (max_ctas > 0 ? max_ctas : 1));
+}
+
+}  // namespace
+
+// ---- geometry --------------------------------------------------------------------------------------------------
+// GS = output pairs, HS = base splits, BPT = bases per lane (multiple of 4), NOP = output pairs per lane.
+bool tab_geometry(int Btot, int out, TabGeom &g) {
+  if (Btot <= 0 || out <= 0) return false;
+  g.GS = (out + 1) / 2;
+  if (g.GS > 32) {
+    g.HS = 1;
+    g.NOP = (g.GS + 31) / 32;
+    g.BPT = ((Btot + 3) / 4) * 4;
+    if (g.NOP == 3) g.NOP = 4;
+    if (!((g.NOP == 2 && g.BPT <= 16) || (g.NOP == 4 && g.BPT <= 8))) return false;
+  } else {
+    g.NOP = 1;
+    const int max_hs = 32 / g.GS;
+    g.HS = 0;
+    for (int hs = 1; hs <= max_hs; ++hs) {
+      const int bpt = (((Btot + hs - 1) / hs + 3) / 4) * 4;
+      if (bpt <= 40) { g.HS = hs; g.BPT = bpt; break; }
+    }
+    if (!g.HS) return false;
+  }
+  // instantiated widths: 4, 8, 16, 24, 32, 40
+  if (g.BPT > 8 && g.BPT <= 16) g.BPT = 16;
+  else if (g.BPT > 16 && g.BPT <= 24) g.BPT = 24;
+  else if (g.BPT > 24 && g.BPT <= 32) g.BPT = 32;
+  else if (g.BPT > 32) g.BPT = 40;
+  const int cs = g.HS * g.BPT;
+  g.CSP = ((cs / 4) & 1) ? cs : cs + 4;   // row pitch with an odd number of 16-byte groups: rows spread over the banks
+  return true;
+}
+
+bool tab_c_geometry(int BI, int out, int &BC, int &OP) {
+  if (BI < 8) return false;       // tiny B: the E x B scratch of the generic path is tiny as well
+  if (out <= 4) { BC = 8; OP = 2; }
+  else if (out <= 10) { BC = 8; OP = 5; }
+  else if (out <= 16) { BC = 4; OP = 8; }
+  else return false;
+  return (BI + BC - 1) / BC <= 32;
+}
+
+#define TAB_DISPATCH(BPTV, NOPV, CALL)                                                                   \
+  do {                                                                                                   \
+    if (geo.NOP == 1) {                                                                                  \
+      switch (geo.BPT) {                                                                                 \
+        case 4: CALL(4, 1); break;                                                                       \
+        case 8: CALL(8, 1); break;                                                                       \
+        case 16: CALL(16, 1); break;                                                                     \
+        case 24: CALL(24, 1); break;                                                                     \
+        case 32: CALL(32, 1); break;                                                                     \
+        default: CALL(40, 1); break;                                                                     \
+      }                                                                                                  \
+    } else if (geo.NOP == 2) {                                                                           \
+      switch (geo.BPT) {                                                                                 \
+        case 4: CALL(4, 2); break;                                                                       \
+        case 8: CALL(8, 2); break;                                                                       \
+        default: CALL(16, 2); break;                                                                     \
+      }                                                                                                  \
+    } else {                                                                                             \
+      switch (geo.BPT) {                                                                                 \
+        case 4: CALL(4, 4); break;                                                                       \
+        default: CALL(8, 4); break;                                                                      \
+      }                                                                                                  \
+    }                                                                                                    \
+  } while (0)
+
+int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, const float *compI, int BI,
+                       const float *TP, const float *compF, int BF, int out, float *msg, cudaStream_t st) {
+  TabGeom geo;
+  MRGCN_REQUIRE(tab_geometry(BI + BF, out, geo), MRGCN_E_NOTSUP, "tab_msg_fwd: unsupported shape B=%d out=%d", BI + BF, out);
+  if (pl->n_tasks == 0) return 0;
+  TabTables tb{TI, TP, BI, BF, out, (int64_t)g->NS};
+  const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
+  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * LT * sizeof(int2);
+  MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_msg_fwd: R*B too large for shared memory (%zu B)", smem);
+  const int ms = msg_stride(out);
+  const int64_t items = cdiv(pl->n_tasks, TPW);
+  MRGCN_PROF("tab_msg_fwd");
+#define CALL(BPTV, NOPV)                                                                                              \
+  do {                                                                                                                \
+    if (int rc = tab_set_smem(k_tab_msg_fwd<BPTV, NOPV>, smem)) return rc;                                            \
+    const unsigned grid = tab_grid(k_tab_msg_fwd<BPTV, NOPV>, smem, cdiv(items, kTabWarps));                          \
+    k_tab_msg_fwd<BPTV, NOPV><<<grid, kTabThreads, smem, st>>>(tb, compI, compF, g->R, g->colptr, pl->task_src,      \
+                                                               pl->task_lo, pl->n_tasks, g->e2_rel, g->e2_val, msg,   \
+                                                               ms, geo.GS, geo.HS, geo.CSP);                          \
+  } while (0)
+  TAB_DISPATCH(BPTV, NOPV, CALL);
+#undef CALL
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *compI, int BI, int out,
+                     const float *gact, float *gW, cudaStream_t st) {
+  TabGeom geo;
+  MRGCN_REQUIRE(tab_geometry(BI, out, geo), MRGCN_E_NOTSUP, "tab_bwd_w: unsupported shape B=%d out=%d", BI, out);
+  if (pl->n_wsrc == 0) return 0;
+  const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
+  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * 32 * sizeof(EdgeMeta);
+  MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_bwd_w: R*B too large for shared memory (%zu B)", smem);
+  const int64_t items = cdiv(pl->n_wsrc, TPW);
+  MRGCN_PROF("tab_bwd_w");
+#define CALL(BPTV, NOPV)                                                                                              \
+  do {                                                                                                                \
+    if (int rc = tab_set_smem(k_tab_bwd_w<BPTV, NOPV>, smem)) return rc;                                              \
+    const unsigned grid = tab_grid(k_tab_bwd_w<BPTV, NOPV>, smem, cdiv(items, kTabWarps));                            \
+    k_tab_bwd_w<BPTV, NOPV><<<grid, kTabThreads, smem, st>>>(compI, g->R, BI, (int64_t)g->NS, out, g->colptr,        \
+                                                             pl->wsrc, pl->n_wsrc, g->e2_dst, g->e2_rel, g->e2_val,   \
+                                                             gact, gW, geo.GS, geo.HS, geo.CSP);                      \
+  } while (0)
+  TAB_DISPATCH(BPTV, NOPV, CALL);
+#undef CALL
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, int BI, int out, const float *gact,
+                     float *rec, cudaStream_t st) {
+  int BC = 0, OP = 0;
+  MRGCN_REQUIRE(tab_c_geometry(BI, out, BC, OP), MRGCN_E_NOTSUP, "tab_bwd_c: unsupported shape B=%d out=%d", BI, out);
+  if (pl->n_tiles == 0) return 0;
+  const int LPT = (BI + BC - 1) / BC, TPW = 32 / LPT;
+  const int BSP = LPT * BC;
+  const size_t smem = ((size_t)pl->tile_slots * BSP) * 4 + (size_t)kTabWarps * TPW * LT * sizeof(int2);
+  MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_bwd_c: tile too large for shared memory (%zu B)", smem);
+  MRGCN_PROF("tab_bwd_c");
+#define CALL(BCV, OPV)                                                                                                 \
+  do {                                                                                                                 \
+    if (int rc = tab_set_smem(k_tab_bwd_c<BCV, OPV>, smem)) return rc;                                                 \
+    const unsigned grid = tab_grid(k_tab_bwd_c<BCV, OPV>, smem, pl->n_tiles);                                          \
+    k_tab_bwd_c<BCV, OPV><<<grid, kTabThreads, smem, st>>>(TI, BI, (int64_t)g->NS, out, g->colptr, pl->task_src,      \
+                                                           pl->task_lo, pl->tile_task_ptr, pl->tile_e0, pl->n_tiles,   \
+                                                           g->e2_dst, g->e2_val, gact, pl->tperm, pl->piece_ptr,       \
+                                                           pl->tile_piece_ptr, rec, LPT, BSP, pl->tile_slots);         \
+  } while (0)
+  if (OP == 2) CALL(8, 2);
+  else if (OP == 5) CALL(8, 5);
+  else CALL(4, 8);
+#undef CALL
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mrgcn
+
+// bit 0: tab_msg_fwd, bit 1: tab_bwd_w (both need B_I + B_F resp. B_I bases to fit the lane geometry),
+// bit 2: tab_bwd_c (no E x B scratch: `cbuf` then holds the n_pieces x B records)
+extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
+  mrgcn::TabGeom geo;
+  int m = 0;
+  if (BI > 0 && mrgcn::tab_geometry(BI + BF, out, geo)) m |= 1;
+  if (BI > 0 && mrgcn::tab_geometry(BI, out, geo)) m |= 2;
+  int BC, OP;
+  if (BI > 0 && mrgcn::tab_c_geometry(BI, out, BC, OP)) m |= 4;
+  return m;
+}

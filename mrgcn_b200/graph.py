@@ -64,6 +64,68 @@ def hub_segments(deg, seg):
     return np.repeat(np.arange(len(d)), nseg), first
 
 
+TAB_LT = 32          # edges per task of the table-term kernels (csrc/tab.cu)
+TAB_TILE = 480       # a tile starts a new one every TAB_TILE edges of E2: at most TAB_TILE + TAB_LT - 1 edges per tile
+TAB_PIECE = 32       # edges per (tile, relation) piece of the comp-gradient reduction
+TAB_WINDOW = 192     # sources per window inside which the basis-gradient kernel orders its tasks by degree
+
+
+def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TILE, piece=TAB_PIECE, window=TAB_WINDOW):
+    """Work plan of the table-term kernels (include/mrgcn_b200.h: mrgcn_tab_plan) from the source-major order E2.
+    Pure torch, any device (the CPU tests check its invariants).  colptr: [NS+1], e2_rel: [>=E] integer tensors."""
+    dev = colptr.device
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    colptr = colptr.long()
+    deg = colptr[1:] - colptr[:-1]
+    ar = lambda n: torch.arange(n, device=dev)
+    # tasks: up to `lt` consecutive edges of one source
+    nt = (deg + lt - 1) // lt
+    first = torch.cumsum(nt, 0) - nt
+    n_tasks = int(nt.sum())
+    task_src = torch.repeat_interleave(ar(NS), nt)
+    task_lo = colptr[task_src] + lt * (ar(n_tasks) - first[task_src])
+    # basis-gradient tasks: one per source that is not a hub, by decreasing degree inside windows of consecutive sources
+    small = torch.nonzero(deg <= long_thresh).flatten()
+    key = (small // window) * (long_thresh + 2) + (long_thresh - deg[small])
+    wsrc = small[torch.argsort(key, stable=True)]
+    plan = dict(n_tasks=n_tasks, lt=lt, task_src=i32(task_src), task_lo=i32(task_lo), wsrc=i32(wsrc), n_wsrc=len(wsrc))
+    if E == 0:
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        plan.update(n_tiles=0, n_pieces=0, tile_slots=lt, tile_task_ptr=z, tile_e0=z, tperm=z, piece_ptr=z, tile_piece_ptr=z,
+                    rel_piece_ptr=torch.zeros(R + 1, dtype=torch.int32, device=dev), rel_piece_idx=z)
+        return plan
+    # tiles: consecutive tasks; a new tile starts whenever a task starts in the next block of `tile` edges
+    _, counts = torch.unique_consecutive(task_lo // tile, return_counts=True)
+    n_tiles = len(counts)
+    tile_task_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(counts, 0)])
+    tile_e0 = task_lo[tile_task_ptr[:-1]]
+    tile_end = torch.cat([tile_e0[1:], torch.tensor([E], device=dev)])
+    tile_slots = int((tile_end - tile_e0).max())
+    tile_of_edge = torch.repeat_interleave(ar(n_tiles), tile_end - tile_e0)
+    # tile-local relation order, cut into pieces of at most `piece` edges of one relation
+    rel = e2_rel[:E].long()
+    order = torch.argsort(tile_of_edge * R + rel, stable=True)          # E2 positions in (tile, relation, position) order
+    ks = (tile_of_edge * R + rel)[order]
+    idx = ar(E)
+    newrun = torch.ones(E, dtype=torch.bool, device=dev)
+    newrun[1:] = ks[1:] != ks[:-1]
+    run_start = torch.cummax(torch.where(newrun, idx, torch.zeros_like(idx)), 0).values
+    newpiece = ((idx - run_start) % piece) == 0
+    piece_start = torch.nonzero(newpiece).flatten()
+    n_pieces = len(piece_start)
+    piece_ptr = torch.cat([piece_start, torch.tensor([E], device=dev)])
+    tperm = order - tile_e0[tile_of_edge[order]]
+    piece_tile = tile_of_edge[order][piece_start]
+    tile_piece_ptr = torch.searchsorted(piece_tile, ar(n_tiles + 1))
+    piece_rel = rel[order][piece_start]
+    rel_piece_idx = torch.argsort(piece_rel, stable=True)
+    rel_piece_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(torch.bincount(piece_rel, minlength=R), 0)])
+    plan.update(n_tiles=n_tiles, n_pieces=n_pieces, tile_slots=tile_slots, tile_task_ptr=i32(tile_task_ptr), tile_e0=i32(tile_e0),
+                tperm=i32(tperm), piece_ptr=i32(piece_ptr), tile_piece_ptr=i32(tile_piece_ptr), rel_piece_ptr=i32(rel_piece_ptr),
+                rel_piece_idx=i32(rel_piece_idx))
+    return plan
+
+
 class RelGraph:
     """E1/E2/E3 edge orders of one adjacency on one CUDA device."""
 
@@ -196,6 +258,22 @@ class RelGraph:
         g = cls.from_coo_arrays(row, col, val, num_nodes, R * num_nodes, R, chunk)
         g.coo = (row, col, val)
         return g
+
+    def tab_plan(self):
+        """Work plan of the table-term kernels over this graph's E2 order (built on first use, then cached)."""
+        if getattr(self, "_tab", None) is None:
+            with torch.cuda.device(self.device):
+                d = build_tab_plan(self.colptr, self.e2_rel, self.E, self.NS, self.R, LONG_THRESH)
+            c = nv.TabPlan()
+            for k in ("n_tasks", "n_wsrc", "n_tiles", "n_pieces", "tile_slots", "lt"):
+                setattr(c, k, int(d[k]))
+            for k in ("task_src", "task_lo", "wsrc", "tile_task_ptr", "tile_e0", "tperm", "piece_ptr", "tile_piece_ptr",
+                      "rel_piece_ptr", "rel_piece_idx"):
+                if d[k].numel() == 0:
+                    d[k] = torch.zeros(1, dtype=_I32, device=self.device)
+                setattr(c, k, d[k].data_ptr())
+            self._tab = (c, d)
+        return self._tab[0]
 
     def to_coo(self, dtype=torch.float32):
         """Back to a (coalesced-order) torch sparse COO on the device: E1 order, column = rel*NS + src."""

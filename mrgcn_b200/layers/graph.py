@@ -5,6 +5,7 @@ runs in hand-written sm_100a kernels behind the C ABI (include/mrgcn_b200.h).  N
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -15,6 +16,13 @@ from ..graph import RelGraph, graph_of
 
 def _empty(n, like_dev):
     return torch.empty(max(int(n), 1), dtype=torch.float32, device=like_dev)
+
+
+def _tab_mode(B, out_dim):
+    """Which table-term kernels (csrc/tab.cu) apply; MRGCN_TAB=0 selects the tile-staging kernels of round 1 (A/B runs)."""
+    if os.environ.get("MRGCN_TAB", "1") == "0":
+        return 0
+    return int(nv.lib().mrgcn_tab_mode(B, 0, out_dim))
 
 
 def _hub_ws(gI, gF, in_dim, out_dim, B, dev):
@@ -62,6 +70,9 @@ class _LayerFn(torch.autograd.Function):
         a.wmix, a.msg_I, a.msg_F, a.out = nv.ptr(wmix), nv.ptr(msg_I), nv.ptr(msg_F), nv.ptr(out)
         hub_ws = _hub_ws(gI if hasI else None, gF if hasF else None, in_dim, out_dim, B, dev)
         a.hub_ws = nv.ptr(hub_ws)
+        # table-term kernels (csrc/tab.cu) for an input layer with basis decomposition
+        plan = gI.tab_plan() if (hasI and B and _tab_mode(B, out_dim)) else None
+        a.plan = C.pointer(plan) if plan is not None else None
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_fwd(C.byref(a), nv.stream_ptr()), "rgcn_layer_fwd")
         ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims = gI, gF, B, bool(relu), (in_dim, out_dim)
@@ -92,12 +103,18 @@ class _LayerFn(torch.autograd.Function):
         g_wI = g_cI = g_wF = g_cF = g_b = g_X = None
         cbuf = g_wmix = None
         part_elems = 1
+        mode = _tab_mode(B, out_dim) if (hasI and B) else 0
+        plan = gI.tab_plan() if mode else None
+        f.plan = C.pointer(plan) if plan is not None else None
         if hasI and (need[1] or need[2]):
             g_wI = torch.empty_like(weight_I)
             if B:
                 g_cI = torch.empty_like(comp_I)
-                cbuf = _empty(gI.E * B, dev)
-                part_elems = max(part_elems, gI.n_chunks * B)
+                if mode & 4:      # records of the (tile, relation) pieces instead of an E x B scratch
+                    cbuf = _empty(plan.n_pieces * B, dev)
+                else:
+                    cbuf = _empty(gI.E * B, dev)
+                    part_elems = max(part_elems, gI.n_chunks * B)
         if hasF and (need[3] or need[4]):
             g_wF = torch.empty_like(weight_F)
             part_elems = max(part_elems, gF.n_chunks * in_dim * out_dim)

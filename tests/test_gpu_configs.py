@@ -57,6 +57,10 @@ def _nc_case(shape, scale, bases=None):
     X = None if fl else torch.randn(N, dims[0])
     lab = torch.arange(0, N, 5)
     tgt = (lab * 7) % dims[-1]
+    # objective = the reference's loss (mean CE over the labelled nodes, checked as a value) + <logits, G> with G ~ N(0,1):
+    # the CE alone back-propagates gradients of 1e-9 .. 1e-13 at these sizes, which any implementation passes under the
+    # absolute 1e-6; the second term makes every gradient O(1) .. O(1e3) so that the element-wise contract bites
+    G = torch.randn(N, dims[-1])
     kw = dict(num_nodes=N, num_relations=R, num_bases=B if B > 0 else -1, featureless=fl)
     res = {}
     for dt in (torch.float32, torch.float64):
@@ -64,7 +68,7 @@ def _nc_case(shape, scale, bases=None):
                   for l in model.rgcn.layers.values()]
         out = rp.rgcn_forward(layers, acts, None if X is None else X.to(dt), A, dtype=dt, **kw)
         loss = rp.nc_loss(out, lab, tgt)
-        loss.backward()
+        (loss + (out * G.to(dt)).sum()).backward()
         res[dt] = (out.detach(), loss.item(), [{k: v.grad for k, v in l.items()} for l in layers])
         del layers, out, loss
     (ref, ref_loss, ref_g), (tru, tru_loss, tru_g) = res[torch.float32], res[torch.float64]
@@ -74,7 +78,7 @@ def _nc_case(shape, scale, bases=None):
     check(out, ref, tru, tag + " logits")
     loss = nn.CrossEntropyLoss()(out[lab.to(DEV)], tgt.to(DEV))
     check_scalar(loss.item(), ref_loss, tru_loss, tag + " loss")
-    loss.backward()
+    (loss + (out * G.to(DEV)).sum()).backward()
     for k, lay in enumerate(model.rgcn.layers.values()):
         for n, p in lay.named_parameters():
             check(p.grad, ref_g[k][n], tru_g[k][n], "%s layer_%d.%s.grad" % (tag, k, n))
@@ -113,6 +117,7 @@ def _lp_case(shape, scale, n_pos=500, n_rank=60):
     c2, Y2 = rp.negative_samples(data, np.random.RandomState(7))
     assert np.array_equal(corrupted, c2) and torch.equal(Y, Y2)
     d, cd = torch.from_numpy(data), torch.as_tensor(corrupted).long()
+    G = torch.randn(N, h)        # second objective term <embeddings, G>: O(1) gradients everywhere (see _nc_case)
     res = {}
     for dt in (torch.float32, torch.float64):
         lay = {k: v.detach().cpu().to(dt).clone().requires_grad_(True) for k, v in model.rgcn.layers["layer_0"].named_parameters()}
@@ -122,7 +127,7 @@ def _lp_case(shape, scale, n_pos=500, n_rank=60):
         sc = torch.cat([rp.distmult_score((d[:, 0], d[:, 1], d[:, 2]), emb, rel),
                         rp.distmult_score((cd[:, 0], cd[:, 1], cd[:, 2]), emb, rel)])
         loss = rp.lp_loss(sc, Y.to(dt))
-        loss.backward()
+        (loss + (emb * G.to(dt)).sum()).backward()
         res[dt] = dict(emb=emb.detach(), sc=sc.detach(), loss=loss.item(), rel=rel.detach(), g_rel=rel.grad,
                        g={k: v.grad for k, v in lay.items()})
         del lay, rel, emb, sc, loss
@@ -135,7 +140,7 @@ def _lp_case(shape, scale, n_pos=500, n_rank=60):
     check(sc, r32["sc"], r64["sc"], tag + " scores")
     loss = nn.BCEWithLogitsLoss()(sc, Y.to(DEV))
     check_scalar(loss.item(), r32["loss"], r64["loss"], tag + " loss")
-    loss.backward()
+    (loss + (emb * G.to(DEV)).sum()).backward()
     check(model.rgcn.relations.grad, r32["g_rel"], r64["g_rel"], tag + " relations.grad")
     for n, p in model.rgcn.layers["layer_0"].named_parameters():
         check(p.grad, r32["g"][n], r64["g"][n], "%s layer_0.%s.grad" % (tag, n))

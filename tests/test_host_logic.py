@@ -82,3 +82,60 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_tab_plan_invariants_and_reduction_semantics():
+    """Work plan of the table-term kernels (mrgcn_b200/graph.py: build_tab_plan, include/mrgcn_b200.h: mrgcn_tab_plan):
+    tasks tile E2 exactly, tiles tile the tasks, every (tile, relation) piece holds <= 32 edges of one relation, and the
+    two-level reduction the comp-gradient kernel performs with it equals the direct per-relation sum."""
+    import torch
+    from mrgcn_b200.graph import build_tab_plan
+    torch.manual_seed(0)
+    NS, R, thresh = 900, 11, 128
+    deg = torch.randint(0, 14, (NS,))
+    deg[5], deg[77], deg[300], deg[301] = 700, 129, 0, 128
+    colptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(deg, 0)])
+    E = int(colptr[-1])
+    rel = torch.cat([torch.sort(torch.randint(0, R, (int(d),))).values for d in deg])
+    p = build_tab_plan(colptr.int(), rel.int(), E, NS, R, thresh)
+    lt = p["lt"]
+    src, lo = p["task_src"].long(), p["task_lo"].long()
+    ln = torch.minimum(torch.full_like(lo, lt), colptr[src + 1] - lo)
+    assert int(ln.min()) >= 1 and int(ln.sum()) == E
+    assert torch.equal(lo[1:], (lo + ln)[:-1]) and int(lo[0]) == 0                 # tasks are consecutive E2 ranges
+    assert bool(((lo >= colptr[src]) & (lo + ln <= colptr[src + 1])).all())        # ... inside their source
+    # basis-gradient tasks: every non-hub source once, degrees non-increasing inside a window
+    w = p["wsrc"].long()
+    assert torch.equal(torch.sort(w).values, torch.nonzero(deg <= thresh).flatten())
+    same_window = (w[1:] // 192) == (w[:-1] // 192)
+    assert bool((deg[w][1:][same_window] <= deg[w][:-1][same_window]).all())
+    # tiles
+    ttp, te0 = p["tile_task_ptr"].long(), p["tile_e0"].long()
+    assert int(ttp[0]) == 0 and int(ttp[-1]) == p["n_tasks"] and bool((ttp[1:] > ttp[:-1]).all())
+    assert torch.equal(te0, lo[ttp[:-1]])
+    tend = torch.cat([te0[1:], torch.tensor([E])])
+    assert int((tend - te0).max()) == p["tile_slots"] <= 480 + lt - 1
+    # pieces: tperm restricted to a tile is a permutation of its slots; a piece has one relation and <= 32 edges
+    tperm, pp, tpp = p["tperm"].long(), p["piece_ptr"].long(), p["tile_piece_ptr"].long()
+    assert int(pp[0]) == 0 and int(pp[-1]) == E and int((pp[1:] - pp[:-1]).max()) <= 32 and int(tpp[-1]) == p["n_pieces"]
+    vals = torch.randn(E, 3, dtype=torch.float64)
+    rec = torch.zeros(p["n_pieces"], 3, dtype=torch.float64)
+    piece_rel = torch.empty(p["n_pieces"], dtype=torch.long)
+    for t in range(p["n_tiles"]):
+        q0, q1 = int(pp[tpp[t]]), int(pp[tpp[t + 1]])
+        assert (q0, q1) == (int(te0[t]), int(tend[t]))
+        assert torch.equal(torch.sort(tperm[q0:q1]).values, torch.arange(q1 - q0))
+        for pc in range(int(tpp[t]), int(tpp[t + 1])):
+            e = te0[t] + tperm[pp[pc]:pp[pc + 1]]
+            assert len(torch.unique(rel[e])) == 1
+            piece_rel[pc] = rel[e[0]]
+            rec[pc] = vals[e].sum(0)
+    rpp, rpi = p["rel_piece_ptr"].long(), p["rel_piece_idx"].long()
+    assert torch.equal(torch.sort(rpi).values, torch.arange(p["n_pieces"]))
+    for r in range(R):
+        mine = rpi[rpp[r]:rpp[r + 1]]
+        assert bool((piece_rel[mine] == r).all())
+        assert torch.allclose(rec[mine].sum(0), vals[rel == r].sum(0), atol=1e-9)
+    # an empty graph gives an empty plan
+    z = build_tab_plan(torch.zeros(5, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), 0, 4, R, thresh)
+    assert z["n_tasks"] == 0 and z["n_tiles"] == 0 and z["n_pieces"] == 0 and z["n_wsrc"] == 4
