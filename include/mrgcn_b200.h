@@ -47,9 +47,6 @@ int64_t mrgcn_launch_count(void);
  * by CUDA events on its own stream.  mrgcn_profile_dump synchronises the device, writes one line per kernel
  * name ("name launches total_ms\n") into buf (NUL terminated, truncated to cap) and clears the records;
  * returns the number of bytes the full text needs. */
-/* Tensor-core (tcgen05, 3xTF32 split) variant of the feature-term message kernel: 0 = never, 1 = whenever it
- * applies (out <= 32), 2 = only where it pays (16 < out <= 32; default, also MRGCN_FEAT_TC in the environment). */
-void mrgcn_set_feat_tc(int mode);
 void mrgcn_profile_enable(int on);
 int64_t mrgcn_profile_dump(char *buf, int64_t cap);
 
@@ -156,6 +153,14 @@ int mrgcn_adjacency_from_triples(const int32_t *triples, int64_t T, int32_t N, i
  * msg_I: workspace [E_I*mrgcn_msg_stride(out)] (only if B>0 and weight_I given); msg_F: workspace
  * [E_F*mrgcn_msg_stride(out)] (per-edge messages, rows padded to 16-byte multiples). */
 int32_t mrgcn_msg_stride(int32_t out);
+/* Per-basis projection of node features on the tensor cores (tcgen05 + tensor-map TMA, split-TF32 with fp32-grade
+ * accuracy): P[j, b*out + o] = sum_k X[j, k] * weight_F[b, k, o].  Replaces the dense half of
+ * torch.einsum('ij,bjk->bik', X, W_F) (mrgcn/layers/graph.py:83-94) after re-association over the bases.
+ * mrgcn_feat_proj_supported returns ceil32(in) (the row pitch X wants) or 0 when the shape is not handled
+ * (in < 32, in > 192, B*out not a multiple of 16 or > 1024). */
+int32_t mrgcn_feat_proj_supported(int32_t in_dim, int32_t B, int32_t out_dim);
+int mrgcn_feat_proj(const float *X, int64_t N, int32_t in_dim, int32_t x_stride, const float *weight_F, int32_t B,
+                    int32_t out_dim, float *vt_ws, float *xpad_ws, float *P, mrgcn_stream_t stream);
 typedef struct mrgcn_layer_args {
   const mrgcn_graph *gI, *gF;
   int32_t in_dim, out_dim, B, relu;
@@ -163,12 +168,15 @@ typedef struct mrgcn_layer_args {
   float *wmix, *msg_I, *msg_F;
   float *hub_ws; /* [max(n_row_segs, n_col_segs) * max(out, in, B*out)] partial sums of hub segments (may be NULL without hubs) */
   float *out; /* [ND, out] */
-  /* table-term kernels (tab.cu): plan of gI (NULL = the tile-staging kernels of round 1);
-   * proj [NS, B, out] workspace: per-basis projection of the features, X . weight_F[b] (feat_proj.cu) - when given
-   * (and the shape fits, mrgcn_tab_mode bit 0 with B_F = B) the feature term of the input layer is mixed together with the
-   * identity term and msg_F is not used; x_stride: row pitch of X in floats (0 = in_dim). */
+  /* table-term kernels (tab.cu): plan of gI (NULL = the tile-staging kernels of round 1).
+   * proj [NS, B, out] workspace: when given (input layer with identity AND feature term, B > 0, gI == gF, and
+   * mrgcn_feat_proj_supported(in, B, out) != 0 and mrgcn_tab_mode(B, B, out) bit 0) the features are projected per basis
+   * on the tensor cores, proj[j, b, :] = X[j, :] . weight_F[b] (feat_proj.cu), and mixed with comp_F in the same pass
+   * that mixes weight_I with comp_I; msg_F is then not used.  vt_ws [2 * B*out * ceil32(in)]: tf32 pieces of weight_F;
+   * xpad_ws [NS * ceil32(in)] or NULL: zero-padded copy of X, needed unless x_stride == ceil32(in) already.
+   * x_stride: row pitch of X in floats (0 = in_dim). */
   const mrgcn_tab_plan *plan;
-  float *proj;
+  float *proj, *vt_ws, *xpad_ws;
   int32_t x_stride, _pad;
 } mrgcn_layer_args;
 int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);

@@ -57,7 +57,8 @@ class LayerArgs(C.Structure):
         ("comp_F", C.c_void_p), ("bias", C.c_void_p), ("row_mask", C.c_void_p), ("addend", C.c_void_p),
         ("wmix", C.c_void_p), ("msg_I", C.c_void_p), ("msg_F", C.c_void_p), ("hub_ws", C.c_void_p),
         ("out", C.c_void_p),
-        ("plan", C.POINTER(TabPlan)), ("proj", C.c_void_p), ("x_stride", C.c_int32), ("_pad", C.c_int32),
+        ("plan", C.POINTER(TabPlan)), ("proj", C.c_void_p), ("vt_ws", C.c_void_p), ("xpad_ws", C.c_void_p),
+        ("x_stride", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -77,7 +78,6 @@ SYMBOLS = {
     "mrgcn_version": (C.c_int, []),
     "mrgcn_last_error_string": (C.c_char_p, []),
     "mrgcn_launch_count": (C.c_int64, []),
-    "mrgcn_set_feat_tc": (None, [C.c_int]),
     "mrgcn_profile_enable": (None, [C.c_int]),
     "mrgcn_profile_dump": (C.c_int64, [C.c_char_p, C.c_int64]),
     "mrgcn_graph_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
@@ -86,6 +86,9 @@ SYMBOLS = {
                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrgcn_msg_stride": (C.c_int32, [C.c_int32]),
     "mrgcn_tab_mode": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "mrgcn_feat_proj_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "mrgcn_feat_proj": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrgcn_rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), C.c_void_p]),
     "mrgcn_rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), C.c_void_p]),
     "mrgcn_distmult_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,

@@ -1,0 +1,379 @@
+// Per-basis projection of the node features on the 5th-generation tensor cores (tcgen05, accumulators in TMEM),
+// operands moved by the TMA engine through tensor maps (cp.async.bulk.tensor, SASS UTMALDG).
+//
+// With basis decomposition the feature term of the input layer (/root/reference/mrgcn/layers/graph.py:83-95) is
+//     X[j,:] . W_F(r) = sum_b comp_F[r,b] * ( X[j,:] . V_F[b] )
+// so the only dense contraction that survives is ONE genuine GEMM over the nodes, not over the edges:
+//     P[j, b*out + o] = sum_k X[j,k] * V_F[b,k,o]            (AM: 1 666 764 x 151 x 400)
+// after which the per-edge work is the same basis mixing the identity term needs (tab.cu mixes both tables in one pass).
+//
+// fp32 parity (1e-5 relative / 1e-6 absolute against the reference's fp32 einsum) rules out plain TF32.  Both operands
+// are split into two tf32 pieces, x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (|x - hi - lo| <= 2^-24 |x|), and
+// three MMAs are issued per K step (hi*hi + lo*hi + hi*lo; the dropped lo*lo is below 2^-22 of the product).  TMEM
+// accumulation rounds toward zero (measured in round 1), so the hi*hi products of every PAIR of 32-wide K chunks get
+// their own accumulator (8 accumulations each), all correction products share one, and the epilogue adds the partial
+// accumulators in registers (round to nearest): the result is as close to the exact product as an fp32 FMA loop is.
+//
+// One persistent CTA per SM; a CTA keeps one NB-column slice of V (both pieces, all K chunks) resident in shared memory
+// and walks the 128-row tiles of X:
+//   warp 4      TMA producer: one 128 x 32 fp32 box of X per stage (tensor map, 128B swizzle = the canonical K-major UMMA
+//               layout, so the raw tile IS the hi operand once rounded in place)
+//   warps 6-9   converters: round the stage to tf32 in place (hi) and write the lo tile next to it; element-wise at the
+//               same byte offset, so the swizzle never has to be computed
+//   warp 5      MMA issuer (one thread) and TMEM owner
+//   warps 0-3   epilogue: tcgen05.ld the 4 partial accumulators, add, release TMEM, store P rows (node-major)
+// mbarrier rings: raw_full (TMA tx) -> conv_done (4 converter warps) -> empty (tcgen05.commit); tmem_full / tmem_empty.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+#include "rgcn_internal.cuh"
+
+namespace mrgcn {
+namespace {
+
+constexpr int BM = 128;               // rows of X per tile (UMMA M)
+constexpr int KCB = 128;              // bytes per row of a K chunk (32 fp32)
+constexpr int A_TILE = BM * KCB;      // 16 KB
+constexpr int SA = 3;                 // A stages
+constexpr int kProjThreads = 320;     // 10 warps
+constexpr int kMaxNKC = 6;
+
+__device__ __forceinline__ uint32_t rna_tf32_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(1024B>>4)<<32 | version 1<<46 | layout 2<<61
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_one(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 2-D tiled TMA load: box at element coordinates (c0 = innermost, c1) of the tensor map -> shared memory
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Vt_hi / Vt_lo [NCpad][KP]: row c = b*out + o holds V[b, 0:in, o] (K-major), split into two tf32 pieces; zero padding
+__global__ void k_vcat_split(const float *__restrict__ V, float *__restrict__ vt_hi, float *__restrict__ vt_lo, int B, int in,
+                             int out, int KP, int NCpad) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= NCpad * KP) return;
+  const int c = x / KP, k = x - c * KP;
+  float w = 0.f;
+  if (c < B * out && k < in) {
+    const int b = c / out, o = c - b * out;
+    w = __ldg(V + ((size_t)b * in + k) * out + o);
+  }
+  const uint32_t h = rna_tf32_bits(w);
+  vt_hi[x] = __uint_as_float(h);
+  vt_lo[x] = __uint_as_float(rna_tf32_bits(w - __uint_as_float(h)));
+}
+
+// X [N][in] -> Xp [N][KP] (zero padded rows of KP floats: 16-byte multiples, what a tensor map needs)
+__global__ void k_pad_rows(const float *__restrict__ X, float *__restrict__ Xp, int64_t N, int in, int ldx, int KP) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= N * KP) return;
+  const int64_t j = x / KP;
+  const int k = (int)(x - j * KP);
+  Xp[x] = k < in ? X[j * ldx + k] : 0.f;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kProjThreads, 1)
+k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmVhi,
+            const __grid_constant__ CUtensorMap tmVlo, float *__restrict__ P, int64_t N, int NC, int NKC, int n_row_tiles,
+            int NCH) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  constexpr int B_TILE = NB * KCB;                         // one K chunk of one piece of the V slice
+  unsigned char *b_hi = base;                              // [NKC][NB rows][128 B]
+  unsigned char *b_lo = b_hi + (size_t)NKC * B_TILE;
+  unsigned char *a_st = b_lo + (size_t)NKC * B_TILE;       // [SA][hi | lo][128 rows][128 B]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(a_st + (size_t)SA * 2 * A_TILE);
+  uint64_t *raw_full = bars, *conv_done = bars + SA, *empty = bars + 2 * SA, *b_full = bars + 3 * SA, *tmem_full = b_full + 1,
+           *tmem_empty = b_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % NCH, rg = blockIdx.x / NCH, GR = gridDim.x / NCH;
+  const int n_my = rg < n_row_tiles ? (n_row_tiles - rg + GR - 1) / GR : 0;
+  const int NG = (NKC + 1) / 2;                            // main accumulators (one per pair of K chunks)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&conv_done[s], 4); mbar_init(&empty[s], 1); }
+    mbar_init(b_full, 1); mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue =====================
+    for (int it = 0; it < n_my; ++it) {
+      const int t = rg + it * GR;
+      mbar_wait(tmem_full, it & 1, 1, 64);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+      float d[NB];
+#pragma unroll
+      for (int cb = 0; cb < NB / 16; ++cb) {
+        uint32_t r[4][16];
+        tmem_ld16(t0 + NG * NB + cb * 16, r[3]);           // correction terms (smallest) first
+#pragma unroll
+        for (int gq = 0; gq < 3; ++gq)
+          if (gq < NG) tmem_ld16(t0 + gq * NB + cb * 16, r[gq]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v = __uint_as_float(r[3][i]);
+#pragma unroll
+          for (int gq = 0; gq < 3; ++gq)
+            if (gq < NG) v += __uint_as_float(r[gq][i]);
+          d[cb * 16 + i] = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_one(tmem_empty);           // TMEM free: the next tile's MMAs overlap the stores below
+      const int64_t j = (int64_t)t * BM + warp * 32 + lane;
+      if (j < N) {
+        float *row = P + j * NC + (size_t)chunk * NB;
+#pragma unroll
+        for (int c = 0; c < NB; c += 4)
+          if (chunk * NB + c < NC) *reinterpret_cast<float4 *>(row + c) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)(2 * NKC * B_TILE));
+      for (int kc = 0; kc < NKC; ++kc) {
+        tma_load_2d(b_hi + (size_t)kc * B_TILE, &tmVhi, kc * 32, chunk * NB, b_full);
+        tma_load_2d(b_lo + (size_t)kc * B_TILE, &tmVlo, kc * 32, chunk * NB, b_full);
+      }
+      int ks = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int t = rg + it * GR;
+        for (int kc = 0; kc < NKC; ++kc, ++ks) {
+          const int s = ks % SA;
+          mbar_wait(&empty[s], ((ks / SA) & 1) ^ 1, 2, 32);
+          mbar_expect_tx(&raw_full[s], A_TILE);
+          tma_load_2d(a_st + (size_t)s * 2 * A_TILE, &tmX, kc * 32, t * BM, &raw_full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(b_full, 0, 3);
+      int ks = 0;
+      for (int it = 0; it < n_my; ++it) {
+        mbar_wait(tmem_empty, (it & 1) ^ 1, 4);
+        tc_fence_after();
+        const uint32_t d_corr = tmem_base + NG * NB;
+        for (int kc = 0; kc < NKC; ++kc, ++ks) {
+          const int s = ks % SA;
+          mbar_wait(&conv_done[s], (ks / SA) & 1, 5);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(a_st + (size_t)s * 2 * A_TILE), a_lo = a_hi + A_TILE;
+          const uint32_t bh = smem_u32(b_hi + (size_t)kc * B_TILE), bl = smem_u32(b_lo + (size_t)kc * B_TILE);
+          const uint32_t d_main = tmem_base + (kc >> 1) * NB;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {     // 4 K steps of 8 tf32 (32 bytes) inside the 128-byte row
+            const uint64_t dah = desc_k_sw128(a_hi + j * 32), dal = desc_k_sw128(a_lo + j * 32);
+            const uint64_t dbh = desc_k_sw128(bh + j * 32), dbl = desc_k_sw128(bl + j * 32);
+            mma_tf32(d_main, dah, dbh, idesc, ((kc & 1) | j) != 0);
+            mma_tf32(d_corr, dal, dbh, idesc, (kc | j) != 0);
+            mma_tf32(d_corr, dah, dbl, idesc, 1);
+          }
+          tc_commit(&empty[s]);          // stage free once these MMAs have read it
+        }
+        tc_commit(tmem_full);            // all accumulators of the tile complete
+      }
+    }
+  } else {
+    // ===================== converters =====================
+    const int cw = warp - 6;             // rows [32 cw, 32 cw + 32) of every stage
+    int ks = 0;
+    for (int it = 0; it < n_my; ++it) {
+      for (int kc = 0; kc < NKC; ++kc, ++ks) {
+        const int s = ks % SA;
+        mbar_wait(&raw_full[s], (ks / SA) & 1, 6);
+        float4 *hi = reinterpret_cast<float4 *>(a_st + (size_t)s * 2 * A_TILE + cw * 4096) + lane;
+        float4 *lo = reinterpret_cast<float4 *>(a_st + (size_t)s * 2 * A_TILE + A_TILE + cw * 4096) + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = hi[i * 32];
+          float4 h, l;
+          h.x = __uint_as_float(rna_tf32_bits(x.x)); l.x = __uint_as_float(rna_tf32_bits(x.x - h.x));
+          h.y = __uint_as_float(rna_tf32_bits(x.y)); l.y = __uint_as_float(rna_tf32_bits(x.y - h.y));
+          h.z = __uint_as_float(rna_tf32_bits(x.z)); l.z = __uint_as_float(rna_tf32_bits(x.z - h.z));
+          h.w = __uint_as_float(rna_tf32_bits(x.w)); l.w = __uint_as_float(rna_tf32_bits(x.w - h.w));
+          hi[i * 32] = h;
+          lo[i * 32] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_one(&conv_done[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 matrix [rows][cols] with row pitch `pitch` floats, boxes of box_rows x 32 floats, 128B swizzle, zero fill out of bounds
+static int make_map(CUtensorMap *m, const float *ptr, int64_t rows, int cols, int pitch, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  MRGCN_REQUIRE(enc, MRGCN_E_NOTSUP, "feat_proj: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MRGCN_REQUIRE(r == CUDA_SUCCESS, MRGCN_E_BADARG, "feat_proj: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static int pick_nb(int NC) {
+  // widest column slice whose 4 accumulators fit the 512 TMEM columns and whose V slice fits shared memory next to the
+  // X stages; NC must be a multiple of it so that every CTA does the same work
+  const int cand[] = {80, 64, 48, 32, 16};
+  for (int nb : cand)
+    if (NC % nb == 0) return nb;
+  return 0;
+}
+
+}  // namespace
+
+bool feat_proj_supported(int in, int ldx, int B, int out) {
+  if (B <= 0 || in < 32 || out <= 0) return false;
+  const int NC = B * out;
+  if (NC % 4 != 0 || NC > 1024 || pick_nb(NC) == 0) return false;
+  const int KP = ((in + 31) / 32) * 32;
+  if (KP / 32 > kMaxNKC) return false;
+  (void)ldx;
+  return true;
+}
+
+// vt_ws: 2 * NC * KP floats.  X rows must be KP = ceil32(in) floats apart with zeros beyond `in` (ldx == KP), or a padded
+// copy is made into xpad_ws [N * KP].
+int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V, int B, int out, float *vt_ws, float *xpad_ws,
+                     float *P, cudaStream_t st) {
+  MRGCN_REQUIRE(feat_proj_supported(in, ldx, B, out), MRGCN_E_NOTSUP, "feat_proj: unsupported shape in=%d B=%d out=%d", in, B, out);
+  if (N == 0) return 0;
+  const int NC = B * out, KP = ((in + 31) / 32) * 32, NKC = KP / 32, NB = pick_nb(NC), NCH = NC / NB;
+  float *vt_hi = vt_ws, *vt_lo = vt_ws + (size_t)NC * KP;
+  MRGCN_PROF("vcat_split");
+  k_vcat_split<<<(unsigned)cdiv((int64_t)NC * KP, 256), 256, 0, st>>>(V, vt_hi, vt_lo, B, in, out, KP, NC);
+  MRGCN_LAUNCH_CHECK();
+  const float *Xp = X;
+  if (ldx != KP) {
+    MRGCN_REQUIRE(xpad_ws, MRGCN_E_BADARG, "feat_proj: X rows are %d floats apart, need %d (or a padding workspace)", ldx, KP);
+    MRGCN_PROF("pad_rows");
+    k_pad_rows<<<(unsigned)cdiv(N * KP, 256), 256, 0, st>>>(X, xpad_ws, N, in, ldx, KP);
+    MRGCN_LAUNCH_CHECK();
+    Xp = xpad_ws;
+  }
+  MRGCN_REQUIRE((reinterpret_cast<uintptr_t>(Xp) & 15) == 0 && (reinterpret_cast<uintptr_t>(vt_ws) & 15) == 0, MRGCN_E_BADARG,
+                "feat_proj: operands must be 16-byte aligned");
+  CUtensorMap tmX, tmVhi, tmVlo;
+  if (int rc = make_map(&tmX, Xp, N, KP, KP, BM)) return rc;
+  if (int rc = make_map(&tmVhi, vt_hi, NC, KP, KP, NB)) return rc;
+  if (int rc = make_map(&tmVlo, vt_lo, NC, KP, KP, NB)) return rc;
+  const int n_row_tiles = (int)cdiv(N, BM);
+  int GR = kNumSMs / NCH;
+  if (GR > n_row_tiles) GR = n_row_tiles;
+  if (GR < 1) GR = 1;
+  const unsigned grid = (unsigned)(GR * NCH);
+  const size_t smem = 1024 + (size_t)2 * NKC * NB * KCB + (size_t)SA * 2 * A_TILE + 256;
+  MRGCN_REQUIRE(smem <= 227 * 1024, MRGCN_E_NOTSUP, "feat_proj: shared memory (%zu B)", smem);
+  MRGCN_PROF("feat_proj");
+#define LAUNCH(NBV)                                                                                                   \
+  do {                                                                                                                \
+    MRGCN_CUDA(cudaFuncSetAttribute(k_feat_proj<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    k_feat_proj<NBV><<<grid, kProjThreads, smem, st>>>(tmX, tmVhi, tmVlo, P, N, NC, NKC, n_row_tiles, NCH);           \
+  } while (0)
+  switch (NB) {
+    case 80: LAUNCH(80); break;
+    case 64: LAUNCH(64); break;
+    case 48: LAUNCH(48); break;
+    case 32: LAUNCH(32); break;
+    default: LAUNCH(16); break;
+  }
+#undef LAUNCH
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mrgcn
+
+using namespace mrgcn;
+
+extern "C" int32_t mrgcn_feat_proj_supported(int32_t in_dim, int32_t B, int32_t out_dim) {
+  return feat_proj_supported(in_dim, 0, B, out_dim) ? ((in_dim + 31) / 32) * 32 : 0;
+}
+
+extern "C" int mrgcn_feat_proj(const float *X, int64_t N, int32_t in_dim, int32_t x_stride, const float *weight_F, int32_t B,
+                               int32_t out_dim, float *vt_ws, float *xpad_ws, float *P, mrgcn_stream_t stream) {
+  MRGCN_REQUIRE(X && weight_F && vt_ws && P, MRGCN_E_BADARG, "feat_proj: null argument");
+  return launch_feat_proj(X, N, in_dim, x_stride > 0 ? x_stride : in_dim, weight_F, B, out_dim, vt_ws, xpad_ws, P,
+                          (cudaStream_t)stream);
+}

@@ -456,7 +456,7 @@ template <int OC>
 __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restrict__ gact,
                              const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ e3_src,
                              const int32_t *__restrict__ e3_dst, const float *__restrict__ e3_val,
-                             float *__restrict__ part, int in, int out) {
+                             float *__restrict__ part, int in, int out, int ldx) {
   __shared__ __align__(16) float Ts[EB * OC];
   __shared__ int Js[EB];
   const int c = blockIdx.x;
@@ -481,7 +481,7 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
       if (kin) {
 #pragma unroll 8
         for (int el = 0; el < EB; ++el) {  // padded entries have t = 0 and read row Js = 0 (valid memory)
-          const float x = X[(size_t)Js[el] * in + k];
+          const float x = X[(size_t)Js[el] * ldx + k];
           const float4 *t4 = reinterpret_cast<const float4 *>(Ts + el * OC);
 #pragma unroll
           for (int q = 0; q < OC / 4; ++q) {
@@ -512,7 +512,7 @@ template <int NK, int OC>
 __global__ void __launch_bounds__(128)
 k_feat_bwd_w_rw(const float *__restrict__ X, const float *__restrict__ gact, const int32_t *__restrict__ chunk_ptr,
                 const int32_t *__restrict__ e3_src, const int32_t *__restrict__ e3_dst,
-                const float *__restrict__ e3_val, float *__restrict__ part, int in, int out) {
+                const float *__restrict__ e3_val, float *__restrict__ part, int in, int out, int ldx) {
   constexpr int P = OC / 2, NW = 4;
   __shared__ __align__(16) float Ts[NW][32][OC];
   __shared__ int Js[NW][32];
@@ -545,7 +545,7 @@ k_feat_bwd_w_rw(const float *__restrict__ X, const float *__restrict__ gact, con
 #pragma unroll
       for (int q = 0; q < NK; ++q) {
         const int k = q * 32 + lane;
-        x[q] = (k < in) ? __ldg(X + (size_t)j * in + k) : 0.f;
+        x[q] = (k < in) ? __ldg(X + (size_t)j * ldx + k) : 0.f;
       }
       float2 t[P];
       if constexpr (OC % 4 == 0) {
@@ -646,6 +646,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   const mrgcn_layer_args &f = a->f;
   const bool hasI = f.weight_I != nullptr, hasF = f.X != nullptr;
   const int B = f.B > 0 ? f.B : 0, out = f.out_dim, in = f.in_dim;
+  const int ldx = f.x_stride > 0 ? f.x_stride : in;
   const mrgcn_graph *gI = f.gI, *gF = f.gF;
   const int ND = hasI ? gI->ND : gF->ND;
   MRGCN_REQUIRE(!f.relu || f.out, MRGCN_E_BADARG, "layer_bwd: relu needs the forward output");
@@ -837,7 +838,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
         MRGCN_PROF("feat_bwd_w");
 #define LAUNCH_RW(NKV, OCV) \
-  k_feat_bwd_w_rw<NKV, OCV><<<(unsigned)gF->n_chunks, 128, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out)
+  k_feat_bwd_w_rw<NKV, OCV><<<(unsigned)gF->n_chunks, 128, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx)
 #define LAUNCH_NK(OCV)                  \
   switch (NK) {                         \
     case 1: LAUNCH_RW(1, OCV); break;   \
@@ -862,10 +863,10 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         dim3 grid((unsigned)gF->n_chunks, (unsigned)cdiv(in, bt));
         MRGCN_PROF("feat_bwd_w");
   switch (OC) {
-          case 4: k_feat_bwd_w<4><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out); break;
-          case 8: k_feat_bwd_w<8><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out); break;
-          case 12: k_feat_bwd_w<12><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out); break;
-          default: k_feat_bwd_w<16><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out); break;
+          case 4: k_feat_bwd_w<4><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx); break;
+          case 8: k_feat_bwd_w<8><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx); break;
+          case 12: k_feat_bwd_w<12><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx); break;
+          default: k_feat_bwd_w<16><<<grid, bt, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx); break;
         }
         MRGCN_LAUNCH_CHECK();
       }
@@ -894,7 +895,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         k_transpose_w<<<dim3((unsigned)cdiv(IO, 128), (unsigned)gF->R), 128, 0, st>>>(W, a->wt_ws, in, out);
         MRGCN_LAUNCH_CHECK();
         if (gF->E > 0)
-          if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
+          if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, out, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
         AggArgs g{};
         g.ND = (int)NS; g.odim = in; g.ms = msg_stride(in); g.out = a->g_X;
         g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;

@@ -191,7 +191,7 @@ template <int OC, int KCT>
 __global__ void __launch_bounds__(kThreads)
 k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const int32_t *__restrict__ chunk_rel,
                const int32_t *__restrict__ chunk_ptr, const int32_t *__restrict__ e3_src,
-               const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP) {  // e3_src: gather index
+               const float *__restrict__ e3_val, float *__restrict__ msg, int in, int out, int INP, int ldx) {  // e3_src: gather index; ldx: row pitch of X
   extern __shared__ __align__(16) float smem[];
   float *Ws = smem;                         // [INP][OC]
   float *Xs_all = smem + (size_t)INP * OC;  // [nwarps][2][32][KCT+1]
@@ -223,7 +223,7 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
           for (int i = 0; i < 32; ++i) {
             const int ji = __shfl_sync(0xffffffffu, j, i);
             const bool ok = ji >= 0 && k < in;
-            cp_async4(dst + i * (KCT + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+            cp_async4(dst + i * (KCT + 1), X + (ok ? (size_t)ji * ldx + k : 0), ok);
           }
         } else {
           const int half = lane >> 4, col = lane & 15;
@@ -233,7 +233,7 @@ k_feat_msg_fwd(const float *__restrict__ X, const float *__restrict__ W, const i
           for (int i = 0; i < 32; i += 2) {
             const int ji = __shfl_sync(0xffffffffu, j, i + half);
             const bool ok = ji >= 0 && k < in;
-            cp_async4(dst + (i + half) * (KCT + 1), X + (ok ? (size_t)ji * in + k : 0), ok);
+            cp_async4(dst + (i + half) * (KCT + 1), X + (ok ? (size_t)ji * ldx + k : 0), ok);
           }
         }
         cp_async_commit();
@@ -566,14 +566,9 @@ static int launch_ident_msg_fwd(const mrgcn_graph *g, const float *V, const floa
   return 0;
 }
 
-int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
+int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, int ldx, const float *W, float *msg, int in,
                     int out, cudaStream_t st, const char *prof_name) {
   if (g->n_chunks == 0) return 0;
-  {
-    int launched = 0;
-    if (int rc = launch_feat_msg_tc(g, gather, X, W, msg, in, out, st, prof_name, &launched)) return rc;
-    if (launched) return 0;
-  }
   const int OC = pick_oc(out);
   const int KCT = in <= 16 ? 16 : KC;
   const int INP = (int)cdiv(in, KCT) * KCT;
@@ -583,7 +578,7 @@ int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X,
   do {                                                                                                             \
     if (int rc = set_smem(k_feat_msg_fwd<OCV, KV>, smem)) return rc;                                               \
     k_feat_msg_fwd<OCV, KV><<<(unsigned)g->n_chunks, kThreads, smem, st>>>(X, W, g->chunk_rel, g->chunk_ptr,      \
-                                                                          gather, g->e3_val, msg, in, out, INP);  \
+                                                                          gather, g->e3_val, msg, in, out, INP, ldx); \
   } while (0)
 #define LAUNCH_K(OCV)                 \
   do {                                \
@@ -644,6 +639,8 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
   MRGCN_REQUIRE(!hasI || a->gI, MRGCN_E_BADARG, "layer_fwd: identity term without graph");
   MRGCN_REQUIRE(!hasF || (a->gF && a->weight_F && a->in_dim > 0), MRGCN_E_BADARG, "layer_fwd: feature term incomplete");
   const int B = a->B > 0 ? a->B : 0, out = a->out_dim, in = a->in_dim;
+  const int ldx = a->x_stride > 0 ? a->x_stride : in;
+  MRGCN_REQUIRE(ldx >= in, MRGCN_E_BADARG, "layer_fwd: x_stride smaller than in_dim");
   const mrgcn_graph *gI = a->gI, *gF = a->gF;
   const int ND = hasI ? gI->ND : gF->ND;
   MRGCN_REQUIRE(!(hasI && hasF) || gI->ND == gF->ND, MRGCN_E_BADARG, "layer_fwd: graphs disagree on rows");
@@ -651,13 +648,22 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
   AggArgs g{};
   g.ND = ND; g.odim = out; g.ms = msg_stride(out); g.relu = a->relu; g.bias = a->bias; g.mask = a->row_mask; g.addend = a->addend; g.out = a->out;
   const mrgcn_graph *gl = hasI ? gI : gF;  // long-row list owner
+  bool fused_feat = false;
   if (hasI) {
     g.rowptr = gI->rowptr;
     if (B > 0) {
       MRGCN_REQUIRE(a->comp_I && a->msg_I, MRGCN_E_BADARG, "layer_fwd: comp_I/msg_I missing");
       TabGeom tg;
+      // projected features: the feature term rides in the identity term's messages (one table pass, one message per edge)
+      fused_feat = hasF && a->proj && a->plan && gI == gF && feat_proj_supported(in, ldx, B, out) && tab_geometry(2 * B, out, tg);
+      if (fused_feat) {
+        MRGCN_REQUIRE(a->comp_F && a->vt_ws, MRGCN_E_BADARG, "layer_fwd: comp_F/vt_ws missing");
+        if (int rc = launch_feat_proj(a->X, gI->NS, in, ldx, a->weight_F, B, out, a->vt_ws, a->xpad_ws, a->proj, st)) return rc;
+      }
       if (gI->E > 0) {
-        if (a->plan && tab_geometry(B, out, tg)) {
+        if (fused_feat) {
+          if (int rc = launch_tab_msg_fwd(gI, a->plan, a->weight_I, a->comp_I, B, a->proj, a->comp_F, B, out, a->msg_I, st)) return rc;
+        } else if (a->plan && tab_geometry(B, out, tg)) {
           if (int rc = launch_tab_msg_fwd(gI, a->plan, a->weight_I, a->comp_I, B, nullptr, nullptr, 0, out, a->msg_I, st)) return rc;
         } else {
           if (int rc = launch_ident_msg_fwd(gI, a->weight_I, a->comp_I, a->msg_I, B, out, st)) return rc;
@@ -675,10 +681,12 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
       if (int rc = launch_basis_mix_fwd(a->comp_F, a->weight_F, a->wmix, gF->R, B, in * out, st)) return rc;
       W = a->wmix;
     }
-    MRGCN_REQUIRE(a->msg_F, MRGCN_E_BADARG, "layer_fwd: msg_F missing");
-    if (gF->E > 0)
-      if (int rc = launch_feat_msg(gF, gF->e3_src, a->X, W, a->msg_F, in, out, st, "feat_msg_fwd")) return rc;
-    g.pF = gF->e1_to_e3; g.msgF = a->msg_F; g.rowptrF = gF->rowptr;
+    if (!fused_feat) {
+      MRGCN_REQUIRE(a->msg_F, MRGCN_E_BADARG, "layer_fwd: msg_F missing");
+      if (gF->E > 0)
+        if (int rc = launch_feat_msg(gF, gF->e3_src, a->X, ldx, W, a->msg_F, in, out, st, "feat_msg_fwd")) return rc;
+      g.pF = gF->e1_to_e3; g.msgF = a->msg_F; g.rowptrF = gF->rowptr;
+    }
   }
   // Long rows are taken from the owner graph (gI when there is an identity term).  The two graphs differ only in
   // mini-batch mode, where gF is a column slice of gI's adjacency, so a row of gF is never longer than the same row of

@@ -46,7 +46,7 @@ struct AggArgs {
 
 int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st);
 // msg[e3,:] = val_e * Xrows[gather[e3], :] . W[r]   (gather = e3_src forward, e3_dst for the input gradient)
-int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
+int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, int ldx, const float *W, float *msg, int in,
                     int out, cudaStream_t st, const char *prof_name);
 // segmented sums of AggArgs over a.ND rows; hub rows (long_rows) are processed one CTA per segment of `seg` edges
 // (seg_hub/seg_first describe the segments), partial sums in hub_ws, combined in segment order
@@ -56,9 +56,10 @@ struct HubSegs {
   float *ws;
 };
 int launch_agg(const AggArgs &a, const HubSegs &h, cudaStream_t st, const char *prof_name);
-// tensor-core (tcgen05, 3xTF32) variant of launch_feat_msg; *launched = 0 when it does not apply
-int launch_feat_msg_tc(const mrgcn_graph *g, const int32_t *gather, const float *X, const float *W, float *msg, int in,
-                       int out, cudaStream_t st, const char *prof_name, int *launched);
+// per-basis projection of the node features on the tensor cores (feat_proj.cu): P[j, b*out + o] = X[j, :] . V[b, :, o]
+bool feat_proj_supported(int in, int ldx, int B, int out);
+int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V, int B, int out, float *vt_ws, float *xpad_ws,
+                     float *P, cudaStream_t st);
 // table-term kernels (tab.cu)
 struct TabGeom { int GS, HS, BPT, NOP, CSP; };
 bool tab_geometry(int Btot, int out, TabGeom &g);

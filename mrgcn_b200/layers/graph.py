@@ -25,6 +25,25 @@ def _tab_mode(B, out_dim):
     return int(nv.lib().mrgcn_tab_mode(B, 0, out_dim))
 
 
+def padded_features(X, pitch=None):
+    """Feature matrix stored with rows of ceil32(in) floats (zeros beyond `in`): the layout the tensor-map TMA loads of
+    the projection kernel (csrc/feat_proj.cu) want.  Returns the (N, in) VIEW of that buffer; handing it to the layer avoids
+    the per-call padding pass (the bench and MRGCN's feature upload do this)."""
+    n, d = X.shape
+    pitch = pitch or ((d + 31) // 32) * 32
+    buf = torch.zeros((n, pitch), dtype=torch.float32, device=X.device)
+    buf[:, :d].copy_(X)
+    return buf[:, :d]
+
+
+def _x_layout(X):
+    """(data tensor handed to the kernels, row pitch in floats).  Accepts contiguous matrices and row-padded views."""
+    if X.dim() == 2 and X.stride(1) == 1 and X.stride(0) >= X.shape[1] and X.storage_offset() % 4 == 0 and X.shape[0] > 1:
+        return X, int(X.stride(0))
+    Xc = X.contiguous()
+    return Xc, int(Xc.shape[1])
+
+
 def _hub_ws(gI, gF, in_dim, out_dim, B, dev):
     """Workspace for the partial sums of hub segments (include/mrgcn_b200.h: hub_ws)."""
     segs = max([max(g.n_row_segs, g.n_col_segs) for g in (gI, gF) if g is not None] + [0])
@@ -46,12 +65,16 @@ class _LayerFn(torch.autograd.Function):
         tens = dict(X=X, weight_I=weight_I, comp_I=comp_I if (hasI and B) else None,
                     weight_F=weight_F if hasF else None, comp_F=comp_F if (hasF and B) else None,
                     bias=bias, row_mask=row_mask, addend=addend)
+        x_stride = 0
         for k, t in tens.items():
             if t is not None:
                 nv.require_cuda(t, k)
                 if t.dtype != torch.float32:
                     raise TypeError("mrgcn_b200: %s must be float32" % k)
-                tens[k] = t.contiguous()
+                if k == "X":
+                    tens[k], x_stride = _x_layout(t)
+                else:
+                    tens[k] = t.contiguous()
         if hasF and tens["X"].shape != (gF.NS, in_dim):
             raise ValueError("X has shape %s, expected (%d, %d)" % (tuple(X.shape), gF.NS, in_dim))
         if hasI and weight_I.shape[0] != (B if B else gI.R) * gI.NS:
@@ -59,23 +82,34 @@ class _LayerFn(torch.autograd.Function):
         out = torch.empty((g0.ND, out_dim), dtype=torch.float32, device=dev)
         wmix = _empty(gF.R * in_dim * out_dim, dev) if (hasF and B) else None
         ms = int(nv.lib().mrgcn_msg_stride(out_dim))
+        # table-term kernels (csrc/tab.cu) for an input layer with basis decomposition
+        plan = gI.tab_plan() if (hasI and B and _tab_mode(B, out_dim)) else None
+        # ... with identity AND feature term: project the features per basis on the tensor cores (csrc/feat_proj.cu) and
+        # mix both tables in one pass; no per-edge feature messages then
+        proj = vt_ws = xpad_ws = None
+        if plan is not None and hasF and gI is gF and os.environ.get("MRGCN_PROJ", "1") != "0":
+            pitch = int(nv.lib().mrgcn_feat_proj_supported(in_dim, B, out_dim))
+            if pitch and (int(nv.lib().mrgcn_tab_mode(B, B, out_dim)) & 1):
+                proj = _empty(gI.NS * B * out_dim, dev)
+                vt_ws = _empty(2 * B * out_dim * pitch, dev)
+                if x_stride != pitch:
+                    xpad_ws = _empty(gI.NS * pitch, dev)
         msg_I = _empty(gI.E * ms, dev) if (hasI and B) else None
-        msg_F = _empty(gF.E * ms, dev) if hasF else None
+        msg_F = _empty(gF.E * ms, dev) if (hasF and proj is None) else None
         a = nv.LayerArgs()
         a.gI = C.pointer(gI.c) if hasI else None
         a.gF = C.pointer(gF.c) if hasF else None
-        a.in_dim, a.out_dim, a.B, a.relu = in_dim, out_dim, B, int(bool(relu))
+        a.in_dim, a.out_dim, a.B, a.relu, a.x_stride = in_dim, out_dim, B, int(bool(relu)), x_stride
         for k, t in tens.items():
             setattr(a, k, nv.ptr(t))
         a.wmix, a.msg_I, a.msg_F, a.out = nv.ptr(wmix), nv.ptr(msg_I), nv.ptr(msg_F), nv.ptr(out)
         hub_ws = _hub_ws(gI if hasI else None, gF if hasF else None, in_dim, out_dim, B, dev)
         a.hub_ws = nv.ptr(hub_ws)
-        # table-term kernels (csrc/tab.cu) for an input layer with basis decomposition
-        plan = gI.tab_plan() if (hasI and B and _tab_mode(B, out_dim)) else None
         a.plan = C.pointer(plan) if plan is not None else None
+        a.proj, a.vt_ws, a.xpad_ws = nv.ptr(proj), nv.ptr(vt_ws), nv.ptr(xpad_ws)
         with torch.cuda.device(dev):
             nv.check(nv.lib().mrgcn_rgcn_layer_fwd(C.byref(a), nv.stream_ptr()), "rgcn_layer_fwd")
-        ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims = gI, gF, B, bool(relu), (in_dim, out_dim)
+        ctx.gI, ctx.gF, ctx.B, ctx.relu, ctx.dims, ctx.x_stride = gI, gF, B, bool(relu), (in_dim, out_dim), x_stride
         ctx.has_addend = addend is not None
         ctx.save_for_backward(tens["X"], tens["weight_I"], tens["comp_I"], tens["weight_F"], tens["comp_F"],
                               tens["bias"], tens["row_mask"], wmix, out)
@@ -94,7 +128,7 @@ class _LayerFn(torch.autograd.Function):
         f = b.f
         f.gI = C.pointer(gI.c) if hasI else None
         f.gF = C.pointer(gF.c) if hasF else None
-        f.in_dim, f.out_dim, f.B, f.relu = in_dim, out_dim, B, int(ctx.relu)
+        f.in_dim, f.out_dim, f.B, f.relu, f.x_stride = in_dim, out_dim, B, int(ctx.relu), ctx.x_stride
         f.weight_I, f.comp_I, f.X, f.weight_F, f.comp_F = (nv.ptr(weight_I), nv.ptr(comp_I), nv.ptr(X),
                                                            nv.ptr(weight_F), nv.ptr(comp_F))
         f.bias, f.row_mask, f.wmix, f.out = nv.ptr(bias), nv.ptr(row_mask), nv.ptr(wmix), nv.ptr(out)
@@ -123,7 +157,7 @@ class _LayerFn(torch.autograd.Function):
                 g_wmix = _empty(gF.R * in_dim * out_dim, dev)
         wt_ws = msgx_ws = None
         if hasF and need[0]:
-            g_X = torch.empty_like(X)
+            g_X = torch.empty(X.shape, dtype=torch.float32, device=dev)
             wt_ws = _empty(gF.R * in_dim * out_dim, dev)
             msgx_ws = _empty(gF.E * int(nv.lib().mrgcn_msg_stride(in_dim)), dev)
         colsum = None

@@ -432,3 +432,53 @@ def test_ranks_vs_oracle():
         ref = rp.compute_ranks(data, E, Rel, 50, filtered).numpy()
         got = lp.compute_ranks_fast(data, E.to(DEV), Rel.to(DEV), 50, filtered).cpu().numpy()
         assert np.array_equal(ref, got)     # integer-valued scores: sums are exact in fp32, so ranks are too
+
+
+@pytest.mark.parametrize("N,indim,B,outdim", [(1000, 151, 40, 10), (130, 145, 2, 200), (4097, 64, 8, 16), (257, 32, 3, 16)])
+def test_feature_projection_tensor_cores(N, indim, B, outdim):
+    """mrgcn_feat_proj (tcgen05 + tensor-map TMA, split TF32): P[j, b, :] = X[j, :] . V[b], element-wise against the fp32
+    matmul of the reference's einsum (graph.py:93) with the float64 product adjudicating."""
+    import ctypes as C
+    from mrgcn_b200 import _native as nv
+    from mrgcn_b200.layers.graph import padded_features
+    torch.manual_seed(N)
+    X = torch.randn(N, indim)
+    X[::7] = 0.0                                   # literal-free nodes carry all-zero feature rows (SURVEY §8d)
+    V = torch.empty(B, indim, outdim)
+    torch.nn.init.xavier_uniform_(V)
+    ref = torch.einsum("ij,bjk->ibk", X, V).reshape(N, B * outdim)
+    tru = torch.einsum("ij,bjk->ibk", X.double(), V.double()).reshape(N, B * outdim)
+    pitch = int(nv.lib().mrgcn_feat_proj_supported(indim, B, outdim))
+    assert pitch == (indim + 31) // 32 * 32
+    Vd = V.to(DEV)
+    for padded in (False, True):
+        Xd = padded_features(X.to(DEV)) if padded else X.to(DEV)
+        P = torch.full((N, B * outdim), float("nan"), device=DEV)
+        vt = torch.empty(2 * B * outdim * pitch, device=DEV)
+        xp = None if padded else torch.empty(N * pitch, device=DEV)
+        nv.check(nv.lib().mrgcn_feat_proj(nv.ptr(Xd), N, indim, Xd.stride(0), nv.ptr(Vd), B, outdim, nv.ptr(vt), nv.ptr(xp),
+                                          nv.ptr(P), nv.stream_ptr()), "feat_proj")
+        check(P, ref, tru, "feat_proj %dx%dx%d%s" % (N, indim, B * outdim, " (padded rows)" if padded else ""))
+
+
+def test_layer_accepts_row_padded_features():
+    """A row-padded view of X (what MRGCN's feature upload and the bench hand over) gives the same result as a contiguous X."""
+    from mrgcn_b200.graph import RelGraph
+    from mrgcn_b200.layers.graph import GraphConvolution, padded_features
+    from mrgcn_b200.synth import synth_triples
+    N, P, B = 3000, 5, 40
+    R = 2 * P + 1
+    rg = RelGraph.from_triples(synth_triples(N, P, 24000, seed=2), N, P)
+    torch.manual_seed(1)
+    layer = GraphConvolution(151, 10, R, N, num_bases=B, bias=True, input_layer=True).to(DEV)
+    X = torch.randn(N, 151, device=DEV)
+    G = torch.randn(N, 10, device=DEV)
+    res = []
+    for Xin in (X, padded_features(X)):
+        for p in layer.parameters():
+            p.grad = None
+        out = layer(Xin, rg)
+        (out * G).sum().backward()
+        res.append([out.detach().clone()] + [p.grad.clone() for p in layer.parameters()])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
