@@ -93,7 +93,7 @@ typedef struct mrgcn_graph {
 /* Work plan of the table-term kernels (tab.cu) over the source-major order E2 of one graph; built by the host side
  * (mrgcn_b200/graph.py: RelGraph.tab_plan) from colptr / e2_rel, once per graph.
  *   task          up to `lt` consecutive E2 edges of one source (a source with more edges has several tasks)
- *   wsrc          the sources with at most long_col_thresh edges, ordered by degree inside windows of 192 sources
+ *   wsrc          the sources with at most long_col_thresh edges (the others are hubs), in node order
  *   tile          consecutive tasks covering at most `tile_slots` E2 edges, one CTA at a time
  *   piece         at most 32 edges of ONE relation inside one tile; tperm lists the tile-local edge slots of every tile
  *                 in (relation, E2 position) order, piece_ptr cuts that list into pieces; the comp gradient of relation

@@ -686,7 +686,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       const int OC = pick_oc(out);
       const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
       TabGeom tg;
-      const bool tab_w = f.plan && tab_geometry(B, out, tg);
+      const bool tab_w = f.plan && tab_geometry(B, out, tg, kBwdWBpt);
       {  // basis gradient
         if (tab_w) {
           if (int rc = launch_tab_bwd_w(gI, f.plan, f.comp_I, B, out, a->gact, a->g_weight_I, st)) return rc;

@@ -62,7 +62,9 @@ int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V,
                      float *P, cudaStream_t st);
 // table-term kernels (tab.cu)
 struct TabGeom { int GS, HS, BPT, NOP, CSP; };
-bool tab_geometry(int Btot, int out, TabGeom &g);
+// max_bpt: widest per-lane base count to prefer (more base splits = fewer registers per lane, more resident warps)
+constexpr int kBwdWBpt = 20;
+bool tab_geometry(int Btot, int out, TabGeom &g, int max_bpt = 40);
 bool tab_c_geometry(int BI, int out, int &BC, int &OP);
 int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, const float *compI, int BI,
                        const float *TP, const float *compF, int BF, int out, float *msg, cudaStream_t st);

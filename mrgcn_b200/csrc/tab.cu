@@ -38,28 +38,15 @@ struct TabTables {
   int64_t NS;
 };
 
-__device__ __forceinline__ const float *tab_row(const TabTables &t, int bb, int64_t j) {
-  return bb < t.BI ? t.TI + ((size_t)bb * t.NS + j) * t.out : t.TP + ((size_t)j * t.BF + (bb - t.BI)) * t.out;
-}
-__device__ __forceinline__ float2 ld_pair(const float *p, int o, int out, bool even) {
-  if (even) return *reinterpret_cast<const float2 *>(p + o);
-  return make_float2(p[o], o + 1 < out ? p[o + 1] : 0.f);
-}
-__device__ __forceinline__ void st_pair(float *p, int o, int out, bool even, float2 v) {
-  if (even) { *reinterpret_cast<float2 *>(p + o) = v; return; }
-  p[o] = v.x;
-  if (o + 1 < out) p[o + 1] = v.y;
-}
-
 // lane geometry shared by the kernels that own (task, output pair, base split)
 struct Geo {
-  int LPT, TPW, tslot, hs, op0;
+  int LPT, TPW, tslot, within, hs, op0;
   bool lane_on;
   __device__ Geo(int GS, int HS, int lane) {
     LPT = GS > 32 ? 32 : GS * HS;
     TPW = 32 / LPT;
     tslot = lane / LPT;
-    const int within = lane - tslot * LPT;
+    within = lane - tslot * LPT;
     hs = GS > 32 ? 0 : within / GS;
     op0 = GS > 32 ? within : within - hs * GS;
     lane_on = tslot < TPW;
@@ -77,8 +64,35 @@ __device__ __forceinline__ void fill_comp(float *comp_s, const float *__restrict
   }
 }
 
+template <bool EVEN>
+__device__ __forceinline__ float2 ld2(const float *p, bool second) {
+  if constexpr (EVEN) return *reinterpret_cast<const float2 *>(p);
+  else return make_float2(p[0], second ? p[1] : 0.f);
+}
+
+// The BPT table rows (x NOP output pairs) of one lane: bases [b0, b0 + BPT) of source j, the first n1 of them from the
+// basis-major identity table, the rest from the node-major projection; everything beyond Btot or `out` is zero.
+template <int BPT, int NOP, bool EVEN>
+__device__ __forceinline__ void load_rows(float2 (&T)[BPT][NOP], const TabTables &tb, int b0, int64_t j, int op0, bool on) {
+  const int out = tb.out, Btot = tb.BI + tb.BF;
+  const int n1 = min(max(tb.BI - b0, 0), BPT);
+  const int nvalid = on ? min(max(Btot - b0, 0), BPT) : 0;
+  const size_t s1 = (size_t)tb.NS * out;
+  const float *p1 = tb.TI + ((size_t)min(b0, tb.BI - 1) * tb.NS + j) * out + 2 * op0;
+  const float *p2 = tb.TP ? tb.TP + ((size_t)j * tb.BF + max(b0 - tb.BI, 0)) * out + 2 * op0 : p1;
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const float *p = b < n1 ? p1 + (size_t)b * s1 : p2 + (ptrdiff_t)(b - n1) * out;
+#pragma unroll
+    for (int q = 0; q < NOP; ++q) {
+      const int o = 2 * (op0 + 32 * q);
+      T[b][q] = (b < nvalid && o < out) ? ld2<EVEN>(p + 64 * q, o + 1 < out) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-template <int BPT, int NOP>
+template <int BPT, int NOP, bool EVEN>
 __global__ void __launch_bounds__(kTabThreads, 2)
 k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__restrict__ compF, int R,
               const int32_t *__restrict__ colptr, const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
@@ -91,41 +105,30 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g(GS, HS, lane);
-  const int Btot = tb.BI + tb.BF, out = tb.out;
-  const bool even = (out & 1) == 0;
-  int2 *wmeta = meta + (size_t)warp * g.TPW * LT;
+  const int out = tb.out;
+  int2 *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task
+  const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_tasks + g.TPW - 1) / g.TPW;
+  const bool writer = g.hs == 0;
+  const bool last_pair = g.op0 == GS - 1;     // (NOP == 1) this lane also zero-fills the row padding
   for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
-    __syncwarp();
-    for (int ts = 0; ts < g.TPW; ++ts) {
-      const int t = wi * g.TPW + ts;
-      if (t < n_tasks) {
-        const int j = task_src[t], lo = task_lo[t];
-        const int len = min(LT, colptr[j + 1] - lo);
-        if (lane < len) wmeta[ts * LT + lane] = make_int2(ldg_stream(e2_rel + lo + lane), __float_as_int(ldg_stream(e2_val + lo + lane)));
-      }
-    }
     const int t = wi * g.TPW + g.tslot;
     const bool on = g.lane_on && t < n_tasks;
     int j = 0, lo = 0, len = 0;
     if (on) { j = task_src[t]; lo = task_lo[t]; len = min(LT, colptr[j + 1] - lo); }
+    __syncwarp();                              // previous item done with the metadata
+    for (int s = g.within; s < len; s += g.LPT)
+      tmeta[s] = make_int2(ldg_stream(e2_rel + lo + s), __float_as_int(ldg_stream(e2_val + lo + s)));
     float2 T[BPT][NOP];
-#pragma unroll
-    for (int b = 0; b < BPT; ++b) {
-      const int bb = g.hs * BPT + b;
-      const float *row = (on && bb < Btot) ? tab_row(tb, bb, j) : nullptr;
-#pragma unroll
-      for (int q = 0; q < NOP; ++q) {
-        const int o = 2 * (g.op0 + 32 * q);
-        T[b][q] = (row && o < out) ? ld_pair(row, o, out, even) : make_float2(0.f, 0.f);
-      }
-    }
+    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, j, g.op0, on);
     __syncwarp();
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    for (int s = 0; s < maxlen; ++s) {
+    float *mrow = msg + (size_t)lo * ms + 2 * g.op0;
+    for (int s = 0; s < maxlen; ++s, mrow += ms) {
       const bool live = s < len;
-      const int2 m = live ? wmeta[g.tslot * LT + s] : make_int2(0, 0);
-      const float *cr = comp_s + (size_t)m.x * CSP + g.hs * BPT;
+      int2 m = make_int2(0, 0);
+      if (live) m = tmeta[s];
+      const float *cr = cbase + m.x * CSP;
       float2 acc[NOP], acc1[NOP];   // two chains per output pair (even / odd groups of four bases), added at the end
 #pragma unroll
       for (int q = 0; q < NOP; ++q) { acc[q] = make_float2(0.f, 0.f); acc1[q] = make_float2(0.f, 0.f); }
@@ -153,18 +156,18 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
           }
         }
       }
-      if (live && g.hs == 0) {
+      if (live && writer) {
         const float v = __int_as_float(m.y);
-        float *row = msg + (size_t)(lo + s) * ms;
+        // rows are padded to `ms` floats (even, >= out): the pad is written as zeros
 #pragma unroll
         for (int q = 0; q < NOP; ++q) {
-          const int op = g.op0 + 32 * q, o = 2 * op;
-          if (o < out) {
-            // rows are padded to `ms` floats (even, >= out): the pad is written as zeros
-            *reinterpret_cast<float2 *>(row + o) = make_float2(v * acc[q].x, o + 1 < out ? v * acc[q].y : 0.f);
-            if (op == GS - 1)
-              for (int z = 2 * GS; z < ms; z += 2) *reinterpret_cast<float2 *>(row + z) = make_float2(0.f, 0.f);
-          }
+          const int o = 2 * (g.op0 + 32 * q);
+          if (o < out) *reinterpret_cast<float2 *>(mrow + 64 * q) = make_float2(v * acc[q].x, (EVEN || o + 1 < out) ? v * acc[q].y : 0.f);
+        }
+        if (last_pair || NOP > 1) {
+          const int z0 = 2 * GS - 2 * g.op0;                 // first pad column, relative to this lane's pointer
+          if (NOP == 1) { for (int z = z0; z < ms - 2 * g.op0; z += 2) *reinterpret_cast<float2 *>(mrow + z) = make_float2(0.f, 0.f); }
+          else if (g.op0 == 0) { for (int z = 2 * GS; z < ms; z += 2) *reinterpret_cast<float2 *>(mrow + z) = make_float2(0.f, 0.f); }
         }
       }
     }
@@ -174,8 +177,8 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
 // ------------------------------------------------------------------------------------------------------------------
 struct __align__(16) EdgeMeta { int d, r; float v; int pad; };
 
-template <int BPT, int NOP>
-__global__ void __launch_bounds__(kTabThreads, (BPT * NOP >= 24) ? 1 : 2)
+template <int BPT, int NOP, bool EVEN>
+__global__ void __launch_bounds__(kTabThreads, (BPT * NOP > 24) ? 1 : 2)
 k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
             const int32_t *__restrict__ wsrc, int n_src, const int32_t *__restrict__ e2_dst,
             const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
@@ -187,8 +190,8 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g(GS, HS, lane);
-  const bool even = (out & 1) == 0;
-  EdgeMeta *wmeta = meta + (size_t)warp * g.TPW * 32;
+  EdgeMeta *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * 32;
+  const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_src + g.TPW - 1) / g.TPW;
   for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
     const int t = wi * g.TPW + g.tslot;
@@ -202,37 +205,34 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
 #pragma unroll
       for (int q = 0; q < NOP; ++q) acc[b][q] = make_float2(0.f, 0.f);
     for (int c0 = 0; c0 < maxlen; c0 += 32) {
+      const int mylen = min(32, max(0, len - c0));
       __syncwarp();
-      for (int ts = 0; ts < g.TPW; ++ts) {
-        const int src_lane = ts * g.LPT;
-        const int lo_ts = __shfl_sync(0xffffffffu, e_lo, src_lane), len_ts = __shfl_sync(0xffffffffu, len, src_lane);
-        if (lane < len_ts - c0) {
-          const int e = lo_ts + c0 + lane;
-          EdgeMeta m;
-          m.d = ldg_stream(e2_dst + e); m.r = ldg_stream(e2_rel + e); m.v = ldg_stream(e2_val + e); m.pad = 0;
-          wmeta[ts * 32 + lane] = m;
-        }
+      for (int s = g.within; s < mylen; s += g.LPT) {
+        const int e = e_lo + c0 + s;
+        EdgeMeta m;
+        m.d = ldg_stream(e2_dst + e); m.r = ldg_stream(e2_rel + e); m.v = ldg_stream(e2_val + e); m.pad = 0;
+        tmeta[s] = m;
       }
       __syncwarp();
       const int nch = min(32, maxlen - c0);
-      const int mylen = min(32, max(0, len - c0));
       for (int s0 = 0; s0 < nch; s0 += 4) {
         EdgeMeta m[4];
         float2 t[4][NOP];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const bool live = s0 + u < mylen;
-          if (live) m[u] = wmeta[g.tslot * 32 + s0 + u];
-          else { m[u].d = 0; m[u].r = 0; m[u].v = 0.f; }
+          m[u].d = 0; m[u].r = 0; m[u].v = 0.f;
+          if (live) m[u] = tmeta[s0 + u];
+          const float *gp = gact + (size_t)m[u].d * out + 2 * g.op0;
 #pragma unroll
           for (int q = 0; q < NOP; ++q) {
             const int o = 2 * (g.op0 + 32 * q);
-            t[u][q] = (live && o < out) ? ld_pair(gact + (size_t)m[u].d * out, o, out, even) : make_float2(0.f, 0.f);
+            t[u][q] = (live && o < out) ? ld2<EVEN>(gp + 64 * q, o + 1 < out) : make_float2(0.f, 0.f);
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float *cr = comp_s + (size_t)m[u].r * CSP + g.hs * BPT;
+          const float *cr = cbase + m[u].r * CSP;
 #pragma unroll
           for (int q = 0; q < NOP; ++q) { t[u][q].x *= m[u].v; t[u][q].y *= m[u].v; }
 #pragma unroll
@@ -250,15 +250,24 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
       }
     }
     if (on) {
+      const int b0 = g.hs * BPT;
+      const size_t s1 = (size_t)NS * out;
+      float *row = gW + ((size_t)b0 * NS + j) * out + 2 * g.op0;
 #pragma unroll
       for (int b = 0; b < BPT; ++b) {
-        const int bb = g.hs * BPT + b;
-        if (bb < BI) {
-          float *row = gW + ((size_t)bb * NS + j) * out;
+        if (b0 + b < BI) {
 #pragma unroll
           for (int q = 0; q < NOP; ++q) {
             const int o = 2 * (g.op0 + 32 * q);
-            if (o < out) st_pair(row, o, out, even, acc[b][q]);
+            if (o < out) {
+              float *p = row + (size_t)b * s1 + 64 * q;
+              if (EVEN || o + 1 < out) {
+                if constexpr (EVEN) *reinterpret_cast<float2 *>(p) = acc[b][q];
+                else { p[0] = acc[b][q].x; p[1] = acc[b][q].y; }
+              } else {
+                p[0] = acc[b][q].x;
+              }
+            }
           }
         }
       }
@@ -267,7 +276,7 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BC, int OP>
+template <int BC, int OP, bool EVEN>
 __global__ void __launch_bounds__(kTabThreads, 2)
 k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
             const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
@@ -282,48 +291,59 @@ k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int
   const int TPW = 32 / LPT;
   const int tslot = lane / LPT, gch = lane - tslot * LPT;   // base chunk of this lane
   const bool lane_on = tslot < TPW;
-  const bool even = (out & 1) == 0;
-  int2 *wmeta = meta + (size_t)warp * TPW * LT;
+  int2 *tmeta = meta + ((size_t)warp * TPW + (lane_on ? tslot : 0)) * LT;
+  const size_t s1 = (size_t)NS * out;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int e0 = tile_e0[tile], t_lo = tile_task_ptr[tile], t_hi = tile_task_ptr[tile + 1];
     const int n_items = (t_hi - t_lo + TPW - 1) / TPW;
     for (int wi = warp; wi < n_items; wi += kTabWarps) {
-      __syncwarp();
-      for (int ts = 0; ts < TPW; ++ts) {
-        const int t = t_lo + wi * TPW + ts;
-        if (t < t_hi) {
-          const int j = task_src[t], lo = task_lo[t];
-          const int len = min(LT, colptr[j + 1] - lo);
-          if (lane < len) wmeta[ts * LT + lane] = make_int2(ldg_stream(e2_dst + lo + lane), __float_as_int(ldg_stream(e2_val + lo + lane)));
-        }
-      }
       const int t = t_lo + wi * TPW + tslot;
       const bool on = lane_on && t < t_hi;
       int j = 0, lo = 0, len = 0;
       if (on) { j = task_src[t]; lo = task_lo[t]; len = min(LT, colptr[j + 1] - lo); }
+      __syncwarp();
+      for (int s = gch; s < len; s += LPT)
+        tmeta[s] = make_int2(ldg_stream(e2_dst + lo + s), __float_as_int(ldg_stream(e2_val + lo + s)));
       float2 T[BC][OP];
+      {
+        const int nvalid = on ? min(max(BI - gch * BC, 0), BC) : 0;
+        const float *p1 = TI + ((size_t)min(gch * BC, BI - 1) * NS + j) * out;
 #pragma unroll
-      for (int b = 0; b < BC; ++b) {
-        const int bb = gch * BC + b;
-        const float *row = (on && bb < BI) ? TI + ((size_t)bb * NS + j) * out : nullptr;
+        for (int b = 0; b < BC; ++b)
 #pragma unroll
-        for (int q = 0; q < OP; ++q) T[b][q] = (row && 2 * q < out) ? ld_pair(row, 2 * q, out, even) : make_float2(0.f, 0.f);
+          for (int q = 0; q < OP; ++q)
+            T[b][q] = (b < nvalid && 2 * q < out) ? ld2<EVEN>(p1 + (size_t)b * s1 + 2 * q, 2 * q + 1 < out) : make_float2(0.f, 0.f);
       }
       __syncwarp();
       const int maxlen = __reduce_max_sync(0xffffffffu, len);
-      for (int s = 0; s < maxlen; ++s) {
-        const bool live = s < len;
-        const int2 m = live ? wmeta[tslot * LT + s] : make_int2(0, 0);
-        const float v = __int_as_float(m.y);
+      // t_e of the next edge is fetched while the current one is multiplied
+      float2 tn[OP];
+      float vn = 0.f;
+      {
+        int2 m = make_int2(0, 0);
+        if (0 < len) m = tmeta[0];
+        vn = __int_as_float(m.y);
         const float *gp = gact + (size_t)m.x * out;
-        float2 tv[OP];
 #pragma unroll
-        for (int q = 0; q < OP; ++q) {
-          tv[q] = (live && 2 * q < out) ? ld_pair(gp, 2 * q, out, even) : make_float2(0.f, 0.f);
-          tv[q].x *= v; tv[q].y *= v;
+        for (int q = 0; q < OP; ++q) tn[q] = (0 < len && 2 * q < out) ? ld2<EVEN>(gp + 2 * q, 2 * q + 1 < out) : make_float2(0.f, 0.f);
+      }
+      float *crow = Cs + (size_t)(lo - e0) * BSP + gch * BC;
+      for (int s = 0; s < maxlen; ++s, crow += BSP) {
+        const bool live = s < len;
+        float2 tv[OP];
+        const float v = vn;
+#pragma unroll
+        for (int q = 0; q < OP; ++q) tv[q] = make_float2(tn[q].x * v, tn[q].y * v);
+        {
+          const bool nlive = s + 1 < len;
+          int2 m = make_int2(0, 0);
+          if (nlive) m = tmeta[s + 1];
+          vn = __int_as_float(m.y);
+          const float *gp = gact + (size_t)m.x * out;
+#pragma unroll
+          for (int q = 0; q < OP; ++q) tn[q] = (nlive && 2 * q < out) ? ld2<EVEN>(gp + 2 * q, 2 * q + 1 < out) : make_float2(0.f, 0.f);
         }
         if (live) {
-          float *crow = Cs + (size_t)(lo + s - e0) * BSP + gch * BC;
 #pragma unroll
           for (int b = 0; b < BC; b += 4) {
             float c[4];
@@ -370,37 +390,40 @@ static unsigned tab_grid(K kernel, size_t smem, int64_t max_ctas) {
 
 // ---- geometry --------------------------------------------------------------------------------------------------
 // GS = output pairs, HS = base splits, BPT = bases per lane (multiple of 4), NOP = output pairs per lane.
-bool tab_geometry(int Btot, int out, TabGeom &g) {
-  if (Btot <= 0 || out <= 0) return false;
-  g.GS = (out + 1) / 2;
+bool tab_geometry(int Btot, int out, TabGeom &g, int max_bpt) {
+  if (Btot <= 0 || out <= 0 || (out & 1)) return false;   // odd widths stay on the tile-staging kernels (8-byte row accesses)
+  g.GS = out / 2;
   if (g.GS > 32) {
     g.HS = 1;
     g.NOP = (g.GS + 31) / 32;
     g.BPT = ((Btot + 3) / 4) * 4;
     if (g.NOP == 3) g.NOP = 4;
-    if (!((g.NOP == 2 && g.BPT <= 16) || (g.NOP == 4 && g.BPT <= 8))) return false;
+    if (g.BPT > 4) g.BPT = 8;
+    if (!((g.NOP == 2 || g.NOP == 4) && Btot <= 8)) return false;
   } else {
     g.NOP = 1;
     const int max_hs = 32 / g.GS;
     g.HS = 0;
     for (int hs = 1; hs <= max_hs; ++hs) {
       const int bpt = (((Btot + hs - 1) / hs + 3) / 4) * 4;
-      if (bpt <= 40) { g.HS = hs; g.BPT = bpt; break; }
+      if (bpt <= max_bpt) { g.HS = hs; g.BPT = bpt; break; }
     }
-    if (!g.HS) return false;
+    if (!g.HS) {   // cannot honour the preferred width: take the widest split
+      g.HS = max_hs;
+      g.BPT = (((Btot + max_hs - 1) / max_hs + 3) / 4) * 4;
+      if (g.BPT > 40) return false;
+    }
+    // instantiated widths: 4, 8, 12, 16, 20, 24, 32, 40
+    if (g.BPT > 24 && g.BPT <= 32) g.BPT = 32;
+    else if (g.BPT > 32) g.BPT = 40;
   }
-  // instantiated widths: 4, 8, 16, 24, 32, 40
-  if (g.BPT > 8 && g.BPT <= 16) g.BPT = 16;
-  else if (g.BPT > 16 && g.BPT <= 24) g.BPT = 24;
-  else if (g.BPT > 24 && g.BPT <= 32) g.BPT = 32;
-  else if (g.BPT > 32) g.BPT = 40;
   const int cs = g.HS * g.BPT;
   g.CSP = ((cs / 4) & 1) ? cs : cs + 4;   // row pitch with an odd number of 16-byte groups: rows spread over the banks
   return true;
 }
 
 bool tab_c_geometry(int BI, int out, int &BC, int &OP) {
-  if (BI < 8) return false;       // tiny B: the E x B scratch of the generic path is tiny as well
+  if (BI < 8 || (out & 1)) return false;   // tiny B: the E x B scratch of the generic path is tiny as well
   if (out <= 4) { BC = 8; OP = 2; }
   else if (out <= 10) { BC = 8; OP = 5; }
   else if (out <= 16) { BC = 4; OP = 8; }
@@ -408,35 +431,30 @@ bool tab_c_geometry(int BI, int out, int &BC, int &OP) {
   return (BI + BC - 1) / BC <= 32;
 }
 
-#define TAB_DISPATCH(BPTV, NOPV, CALL)                                                                   \
+#define TAB_DISPATCH(CALL)                                                                               \
   do {                                                                                                   \
     if (geo.NOP == 1) {                                                                                  \
       switch (geo.BPT) {                                                                                 \
         case 4: CALL(4, 1); break;                                                                       \
         case 8: CALL(8, 1); break;                                                                       \
+        case 12: CALL(12, 1); break;                                                                     \
         case 16: CALL(16, 1); break;                                                                     \
+        case 20: CALL(20, 1); break;                                                                     \
         case 24: CALL(24, 1); break;                                                                     \
         case 32: CALL(32, 1); break;                                                                     \
         default: CALL(40, 1); break;                                                                     \
       }                                                                                                  \
     } else if (geo.NOP == 2) {                                                                           \
-      switch (geo.BPT) {                                                                                 \
-        case 4: CALL(4, 2); break;                                                                       \
-        case 8: CALL(8, 2); break;                                                                       \
-        default: CALL(16, 2); break;                                                                     \
-      }                                                                                                  \
+      if (geo.BPT == 4) CALL(4, 2); else CALL(8, 2);                                                     \
     } else {                                                                                             \
-      switch (geo.BPT) {                                                                                 \
-        case 4: CALL(4, 4); break;                                                                       \
-        default: CALL(8, 4); break;                                                                      \
-      }                                                                                                  \
+      if (geo.BPT == 4) CALL(4, 4); else CALL(8, 4);                                                     \
     }                                                                                                    \
   } while (0)
 
 int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, const float *compI, int BI,
                        const float *TP, const float *compF, int BF, int out, float *msg, cudaStream_t st) {
   TabGeom geo;
-  MRGCN_REQUIRE(tab_geometry(BI + BF, out, geo), MRGCN_E_NOTSUP, "tab_msg_fwd: unsupported shape B=%d out=%d", BI + BF, out);
+  MRGCN_REQUIRE(tab_geometry(BI + BF, out, geo, 40), MRGCN_E_NOTSUP, "tab_msg_fwd: unsupported shape B=%d out=%d", BI + BF, out);
   if (pl->n_tasks == 0) return 0;
   TabTables tb{TI, TP, BI, BF, out, (int64_t)g->NS};
   const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
@@ -447,13 +465,13 @@ int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const flo
   MRGCN_PROF("tab_msg_fwd");
 #define CALL(BPTV, NOPV)                                                                                              \
   do {                                                                                                                \
-    if (int rc = tab_set_smem(k_tab_msg_fwd<BPTV, NOPV>, smem)) return rc;                                            \
-    const unsigned grid = tab_grid(k_tab_msg_fwd<BPTV, NOPV>, smem, cdiv(items, kTabWarps));                          \
-    k_tab_msg_fwd<BPTV, NOPV><<<grid, kTabThreads, smem, st>>>(tb, compI, compF, g->R, g->colptr, pl->task_src,      \
+    if (int rc = tab_set_smem(k_tab_msg_fwd<BPTV, NOPV, true>, smem)) return rc;                                            \
+    const unsigned grid = tab_grid(k_tab_msg_fwd<BPTV, NOPV, true>, smem, cdiv(items, kTabWarps));                          \
+    k_tab_msg_fwd<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(tb, compI, compF, g->R, g->colptr, pl->task_src,      \
                                                                pl->task_lo, pl->n_tasks, g->e2_rel, g->e2_val, msg,   \
                                                                ms, geo.GS, geo.HS, geo.CSP);                          \
   } while (0)
-  TAB_DISPATCH(BPTV, NOPV, CALL);
+  TAB_DISPATCH(CALL);
 #undef CALL
   MRGCN_LAUNCH_CHECK();
   return 0;
@@ -462,7 +480,7 @@ int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const flo
 int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *compI, int BI, int out,
                      const float *gact, float *gW, cudaStream_t st) {
   TabGeom geo;
-  MRGCN_REQUIRE(tab_geometry(BI, out, geo), MRGCN_E_NOTSUP, "tab_bwd_w: unsupported shape B=%d out=%d", BI, out);
+  MRGCN_REQUIRE(tab_geometry(BI, out, geo, kBwdWBpt), MRGCN_E_NOTSUP, "tab_bwd_w: unsupported shape B=%d out=%d", BI, out);
   if (pl->n_wsrc == 0) return 0;
   const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
   const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * 32 * sizeof(EdgeMeta);
@@ -471,13 +489,13 @@ int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
   MRGCN_PROF("tab_bwd_w");
 #define CALL(BPTV, NOPV)                                                                                              \
   do {                                                                                                                \
-    if (int rc = tab_set_smem(k_tab_bwd_w<BPTV, NOPV>, smem)) return rc;                                              \
-    const unsigned grid = tab_grid(k_tab_bwd_w<BPTV, NOPV>, smem, cdiv(items, kTabWarps));                            \
-    k_tab_bwd_w<BPTV, NOPV><<<grid, kTabThreads, smem, st>>>(compI, g->R, BI, (int64_t)g->NS, out, g->colptr,        \
+    if (int rc = tab_set_smem(k_tab_bwd_w<BPTV, NOPV, true>, smem)) return rc;                                              \
+    const unsigned grid = tab_grid(k_tab_bwd_w<BPTV, NOPV, true>, smem, cdiv(items, kTabWarps));                            \
+    k_tab_bwd_w<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(compI, g->R, BI, (int64_t)g->NS, out, g->colptr,        \
                                                              pl->wsrc, pl->n_wsrc, g->e2_dst, g->e2_rel, g->e2_val,   \
                                                              gact, gW, geo.GS, geo.HS, geo.CSP);                      \
   } while (0)
-  TAB_DISPATCH(BPTV, NOPV, CALL);
+  TAB_DISPATCH(CALL);
 #undef CALL
   MRGCN_LAUNCH_CHECK();
   return 0;
@@ -495,9 +513,9 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
   MRGCN_PROF("tab_bwd_c");
 #define CALL(BCV, OPV)                                                                                                 \
   do {                                                                                                                 \
-    if (int rc = tab_set_smem(k_tab_bwd_c<BCV, OPV>, smem)) return rc;                                                 \
-    const unsigned grid = tab_grid(k_tab_bwd_c<BCV, OPV>, smem, pl->n_tiles);                                          \
-    k_tab_bwd_c<BCV, OPV><<<grid, kTabThreads, smem, st>>>(TI, BI, (int64_t)g->NS, out, g->colptr, pl->task_src,      \
+    if (int rc = tab_set_smem(k_tab_bwd_c<BCV, OPV, true>, smem)) return rc;                                                 \
+    const unsigned grid = tab_grid(k_tab_bwd_c<BCV, OPV, true>, smem, pl->n_tiles);                                          \
+    k_tab_bwd_c<BCV, OPV, true><<<grid, kTabThreads, smem, st>>>(TI, BI, (int64_t)g->NS, out, g->colptr, pl->task_src,      \
                                                            pl->task_lo, pl->tile_task_ptr, pl->tile_e0, pl->n_tiles,   \
                                                            g->e2_dst, g->e2_val, gact, pl->tperm, pl->piece_ptr,       \
                                                            pl->tile_piece_ptr, rec, LPT, BSP, pl->tile_slots);         \
@@ -517,8 +535,8 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
 extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
   mrgcn::TabGeom geo;
   int m = 0;
-  if (BI > 0 && mrgcn::tab_geometry(BI + BF, out, geo)) m |= 1;
-  if (BI > 0 && mrgcn::tab_geometry(BI, out, geo)) m |= 2;
+  if (BI > 0 && mrgcn::tab_geometry(BI + BF, out, geo, 40)) m |= 1;
+  if (BI > 0 && mrgcn::tab_geometry(BI, out, geo, mrgcn::kBwdWBpt)) m |= 2;
   int BC, OP;
   if (BI > 0 && mrgcn::tab_c_geometry(BI, out, BC, OP)) m |= 4;
   return m;

@@ -67,10 +67,9 @@ def hub_segments(deg, seg):
 TAB_LT = 32          # edges per task of the table-term kernels (csrc/tab.cu)
 TAB_TILE = 480       # a tile starts a new one every TAB_TILE edges of E2: at most TAB_TILE + TAB_LT - 1 edges per tile
 TAB_PIECE = 32       # edges per (tile, relation) piece of the comp-gradient reduction
-TAB_WINDOW = 192     # sources per window inside which the basis-gradient kernel orders its tasks by degree
 
 
-def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TILE, piece=TAB_PIECE, window=TAB_WINDOW):
+def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TILE, piece=TAB_PIECE):
     """Work plan of the table-term kernels (include/mrgcn_b200.h: mrgcn_tab_plan) from the source-major order E2.
     Pure torch, any device (the CPU tests check its invariants).  colptr: [NS+1], e2_rel: [>=E] integer tensors."""
     dev = colptr.device
@@ -84,10 +83,10 @@ def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TI
     n_tasks = int(nt.sum())
     task_src = torch.repeat_interleave(ar(NS), nt)
     task_lo = colptr[task_src] + lt * (ar(n_tasks) - first[task_src])
-    # basis-gradient tasks: one per source that is not a hub, by decreasing degree inside windows of consecutive sources
-    small = torch.nonzero(deg <= long_thresh).flatten()
-    key = (small // window) * (long_thresh + 2) + (long_thresh - deg[small])
-    wsrc = small[torch.argsort(key, stable=True)]
+    # basis-gradient tasks: one per source that is not a hub, in node order (neighbouring lanes own neighbouring rows of
+    # the gradient: their 8-byte stores fill whole sectors; ordering by degree was measured to turn them into
+    # read-modify-write traffic, profiles/r02d_ncu_full_summary.txt)
+    wsrc = torch.nonzero(deg <= long_thresh).flatten()
     plan = dict(n_tasks=n_tasks, lt=lt, task_src=i32(task_src), task_lo=i32(task_lo), wsrc=i32(wsrc), n_wsrc=len(wsrc))
     if E == 0:
         z = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -35,3 +35,17 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return load
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Persist the element-wise parity report (tests/parity.py) of a GPU run: gpurun_out/parity_report.txt travels back from
+    the GPU box and is copied to profiles/ by hand."""
+    try:
+        import parity
+    except ImportError:
+        return
+    if parity.REPORT:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.txt"), "w") as f:
+            f.write("\n".join(parity.REPORT) + "\n")
