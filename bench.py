@@ -266,7 +266,10 @@ def main():
         Xh = torch.empty((N, dims[0]), dtype=torch.float32).pin_memory()
         g = torch.Generator().manual_seed(1)       # identical features on every rank
         Xh.normal_(generator=g)
-    Xd = Xh.to(dev) if Xh is not None else None
+    # device-resident features live in rows of ceil32(in) floats (what the projection kernel's tensor-map loads read);
+    # the e2e path uploads into the same layout every step (MRGCN._upload_features)
+    from mrgcn_b200.layers.graph import padded_features
+    Xd = padded_features(Xh.to(dev)) if Xh is not None else None
     ce = nn.CrossEntropyLoss(reduction="sum")
 
     if world == 1:

@@ -97,7 +97,9 @@ typedef struct mrgcn_graph {
  *   tile          consecutive tasks covering at most `tile_slots` E2 edges, one CTA at a time
  *   piece         at most 32 edges of ONE relation inside one tile; tperm lists the tile-local edge slots of every tile
  *                 in (relation, E2 position) order, piece_ptr cuts that list into pieces; the comp gradient of relation
- *                 r is the sum, in rel_piece_idx order, of the records of its pieces. */
+ *                 r is the sum of the records of its pieces, taken in two fixed-order stages: rel_piece_idx lists the pieces
+ *                 relation by relation, blk_ptr cuts that list into blocks of at most 128 pieces of one relation, and
+ *                 rel_blk_ptr[r .. r+1] is the range of blocks of relation r. */
 typedef struct mrgcn_tab_plan {
   int32_t n_tasks, n_wsrc, n_tiles, n_pieces, tile_slots, lt, _pad0, _pad1;
   int32_t *task_src, *task_lo;   /* [n_tasks] source and first E2 edge of task t */
@@ -109,6 +111,9 @@ typedef struct mrgcn_tab_plan {
   int32_t *tile_piece_ptr;       /* [n_tiles+1] */
   int32_t *rel_piece_ptr;        /* [R+1] */
   int32_t *rel_piece_idx;        /* [n_pieces] */
+  int32_t *blk_ptr;              /* [n_blks+1] positions in rel_piece_idx */
+  int32_t *rel_blk_ptr;          /* [R+1] */
+  int32_t n_blks, _pad2;
 } mrgcn_tab_plan;
 /* which table-term kernels apply to (B_I identity bases, B_F projected feature bases, out): bit 0 forward messages,
  * bit 1 basis gradient, bit 2 comp gradient without the E x B scratch (cbuf then holds n_pieces x B records). */
@@ -161,6 +166,9 @@ int32_t mrgcn_msg_stride(int32_t out);
 int32_t mrgcn_feat_proj_supported(int32_t in_dim, int32_t B, int32_t out_dim);
 int mrgcn_feat_proj(const float *X, int64_t N, int32_t in_dim, int32_t x_stride, const float *weight_F, int32_t B,
                     int32_t out_dim, float *vt_ws, float *xpad_ws, float *P, mrgcn_stream_t stream);
+/* Pinned host rows [rows][cols] -> device rows of `pitch` floats (cudaMemcpy2DAsync on `stream`); pad columns untouched.
+ * The feature upload of MRGCN.forward (mrgcn/models/mrgcn.py:203-204) in the layout mrgcn_feat_proj reads. */
+int mrgcn_upload_rows(const float *X_host, int64_t rows, int32_t cols, float *X_dev, int32_t pitch, mrgcn_stream_t stream);
 typedef struct mrgcn_layer_args {
   const mrgcn_graph *gI, *gF;
   int32_t in_dim, out_dim, B, relu;
@@ -186,7 +194,7 @@ int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t stream);
  * Gradients are written (not accumulated); NULL pointer = not wanted.
  *   g_weight_I [S*NS_I,out]  g_comp_I [R,B]  g_weight_F [S,in,out]  g_comp_F [R,B]  g_bias [out]
  *   g_X [NS_F,in]
- * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term; [n_pieces*B] when f.plan is given and
+ * Workspaces: gact [ND*out]; cbuf [E_I*B] (B>0 and identity term; [(n_pieces + n_blks)*B] when f.plan is given and
  *   mrgcn_tab_mode(B, 0, out) has bit 2);
  *   part [n_chunks * max(B, in*out)] ; g_wmix [R*in*out] (B>0 and feature term);
  *   colsum_ws [ceil(ND/1024) * out]; wt_ws, msgx_ws when g_X is wanted. */

@@ -44,7 +44,8 @@ class TabPlan(C.Structure):
         ("tile_slots", C.c_int32), ("lt", C.c_int32), ("_pad0", C.c_int32), ("_pad1", C.c_int32),
         ("task_src", C.c_void_p), ("task_lo", C.c_void_p), ("wsrc", C.c_void_p), ("tile_task_ptr", C.c_void_p),
         ("tile_e0", C.c_void_p), ("tperm", C.c_void_p), ("piece_ptr", C.c_void_p), ("tile_piece_ptr", C.c_void_p),
-        ("rel_piece_ptr", C.c_void_p), ("rel_piece_idx", C.c_void_p),
+        ("rel_piece_ptr", C.c_void_p), ("rel_piece_idx", C.c_void_p), ("blk_ptr", C.c_void_p), ("rel_blk_ptr", C.c_void_p),
+        ("n_blks", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -89,6 +90,7 @@ SYMBOLS = {
     "mrgcn_feat_proj_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgcn_feat_proj": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrgcn_upload_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "mrgcn_rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), C.c_void_p]),
     "mrgcn_rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), C.c_void_p]),
     "mrgcn_distmult_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,

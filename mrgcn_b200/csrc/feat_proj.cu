@@ -15,14 +15,16 @@
 // accumulators in registers (round to nearest): the result is as close to the exact product as an fp32 FMA loop is.
 //
 // One persistent CTA per SM; a CTA keeps one NB-column slice of V (both pieces, all K chunks) resident in shared memory
-// and walks the 128-row tiles of X:
-//   warp 4      TMA producer: one 128 x 32 fp32 box of X per stage (tensor map, 128B swizzle = the canonical K-major UMMA
-//               layout, so the raw tile IS the hi operand once rounded in place)
-//   warps 6-9   converters: round the stage to tf32 in place (hi) and write the lo tile next to it; element-wise at the
-//               same byte offset, so the swizzle never has to be computed
-//   warp 5      MMA issuer (one thread) and TMEM owner
+// and walks the 128-row tiles of X.  The A operand is fed from TENSOR MEMORY: shared memory then only holds the raw fp32
+// tiles on their way in (6 x 16 KB in flight per SM - the loads are latency-bound, profiles/r02d_ncu_full_summary.txt) and
+// the MMA reads nothing but the V slice from shared memory.
+//   warp 4      TMA producer: one 128 x 32 fp32 box of X per stage (tensor map, 128B swizzle)
+//   warps 6-9   converters: lane = row; read the row's 32 values (un-swizzling the 16-byte chunks), split them into the
+//               tf32 pieces hi / lo in registers and tcgen05.st both into a ring of 3 TMEM stages (64 columns each)
+//   warp 5      MMA issuer (one thread) and TMEM owner: D[tmem] += A[tmem] . B[smem]
 //   warps 0-3   epilogue: tcgen05.ld the 4 partial accumulators, add, release TMEM, store P rows (node-major)
-// mbarrier rings: raw_full (TMA tx) -> conv_done (4 converter warps) -> empty (tcgen05.commit); tmem_full / tmem_empty.
+// mbarrier rings: raw_full (TMA tx) / raw_empty (4 converter warps), a_full (4 converter warps) / a_empty (tcgen05.commit),
+// tmem_full / tmem_empty.  TMEM columns: 4 x NB accumulators + 3 x 64 operand stages <= 512.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -36,7 +38,8 @@ namespace {
 constexpr int BM = 128;               // rows of X per tile (UMMA M)
 constexpr int KCB = 128;              // bytes per row of a K chunk (32 fp32)
 constexpr int A_TILE = BM * KCB;      // 16 KB
-constexpr int SA = 3;                 // A stages
+constexpr int RS = 6;                 // raw X stages in shared memory (TMA destinations)
+constexpr int AS = 3;                 // operand stages in tensor memory (hi | lo, 64 columns each)
 constexpr int kProjThreads = 320;     // 10 warps
 constexpr int kMaxNKC = 6;
 
@@ -47,16 +50,28 @@ __device__ __forceinline__ uint64_t desc_k_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[tmem] . B[smem]: A = 128 lanes x 8 columns (one tf32 per column) at a_tmem
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+      "%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -118,18 +133,20 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   constexpr int B_TILE = NB * KCB;                         // one K chunk of one piece of the V slice
   unsigned char *b_hi = base;                              // [NKC][NB rows][128 B]
   unsigned char *b_lo = b_hi + (size_t)NKC * B_TILE;
-  unsigned char *a_st = b_lo + (size_t)NKC * B_TILE;       // [SA][hi | lo][128 rows][128 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(a_st + (size_t)SA * 2 * A_TILE);
-  uint64_t *raw_full = bars, *conv_done = bars + SA, *empty = bars + 2 * SA, *b_full = bars + 3 * SA, *tmem_full = b_full + 1,
-           *tmem_empty = b_full + 2;
+  unsigned char *a_raw = b_lo + (size_t)NKC * B_TILE;      // [RS][128 rows][128 B] raw fp32, 128B-swizzled by the TMA
+  uint64_t *bars = reinterpret_cast<uint64_t *>(a_raw + (size_t)RS * A_TILE);
+  uint64_t *raw_full = bars, *raw_empty = bars + RS, *a_full = bars + 2 * RS, *a_empty = a_full + AS, *b_full = a_empty + AS,
+           *tmem_full = b_full + 1, *tmem_empty = b_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % NCH, rg = blockIdx.x / NCH, GR = gridDim.x / NCH;
   const int n_my = rg < n_row_tiles ? (n_row_tiles - rg + GR - 1) / GR : 0;
   const int NG = (NKC + 1) / 2;                            // main accumulators (one per pair of K chunks)
+  constexpr int A_COL0 = 4 * NB;                           // operand stages behind the (at most) 4 accumulators
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&conv_done[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
     mbar_init(b_full, 1); mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
     mbar_fence_init();
   }
@@ -190,10 +207,10 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       for (int it = 0; it < n_my; ++it) {
         const int t = rg + it * GR;
         for (int kc = 0; kc < NKC; ++kc, ++ks) {
-          const int s = ks % SA;
-          mbar_wait(&empty[s], ((ks / SA) & 1) ^ 1, 2, 32);
+          const int s = ks % RS;
+          mbar_wait(&raw_empty[s], ((ks / RS) & 1) ^ 1, 2, 32);
           mbar_expect_tx(&raw_full[s], A_TILE);
-          tma_load_2d(a_st + (size_t)s * 2 * A_TILE, &tmX, kc * 32, t * BM, &raw_full[s]);
+          tma_load_2d(a_raw + (size_t)s * A_TILE, &tmX, kc * 32, t * BM, &raw_full[s]);
         }
       }
     }
@@ -208,49 +225,57 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_corr = tmem_base + NG * NB;
         for (int kc = 0; kc < NKC; ++kc, ++ks) {
-          const int s = ks % SA;
-          mbar_wait(&conv_done[s], (ks / SA) & 1, 5);
+          const int s = ks % AS;
+          mbar_wait(&a_full[s], (ks / AS) & 1, 5);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_st + (size_t)s * 2 * A_TILE), a_lo = a_hi + A_TILE;
+          const uint32_t a_hi = tmem_base + A_COL0 + s * 64, a_lo = a_hi + 32;
           const uint32_t bh = smem_u32(b_hi + (size_t)kc * B_TILE), bl = smem_u32(b_lo + (size_t)kc * B_TILE);
           const uint32_t d_main = tmem_base + (kc >> 1) * NB;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {     // 4 K steps of 8 tf32 (32 bytes) inside the 128-byte row
-            const uint64_t dah = desc_k_sw128(a_hi + j * 32), dal = desc_k_sw128(a_lo + j * 32);
+          for (int j = 0; j < 4; ++j) {     // 4 K steps of 8 tf32: 8 TMEM columns of A, 32 bytes of every B row
             const uint64_t dbh = desc_k_sw128(bh + j * 32), dbl = desc_k_sw128(bl + j * 32);
-            mma_tf32(d_main, dah, dbh, idesc, ((kc & 1) | j) != 0);
-            mma_tf32(d_corr, dal, dbh, idesc, (kc | j) != 0);
-            mma_tf32(d_corr, dah, dbl, idesc, 1);
+            mma_tf32_ts(d_main, a_hi + j * 8, dbh, idesc, ((kc & 1) | j) != 0);
+            mma_tf32_ts(d_corr, a_lo + j * 8, dbh, idesc, (kc | j) != 0);
+            mma_tf32_ts(d_corr, a_hi + j * 8, dbl, idesc, 1);
           }
-          tc_commit(&empty[s]);          // stage free once these MMAs have read it
+          tc_commit(&a_empty[s]);        // operand stage free once these MMAs have read it
         }
         tc_commit(tmem_full);            // all accumulators of the tile complete
       }
     }
   } else {
     // ===================== converters =====================
-    const int cw = warp - 6;             // rows [32 cw, 32 cw + 32) of every stage
+    const int q4 = warp & 3;             // TMEM lane quarter this warp may access = rows [32 q4, 32 q4 + 32) of the tile
+    const int row = q4 * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16) + A_COL0;
     int ks = 0;
     for (int it = 0; it < n_my; ++it) {
       for (int kc = 0; kc < NKC; ++kc, ++ks) {
-        const int s = ks % SA;
-        mbar_wait(&raw_full[s], (ks / SA) & 1, 6);
-        float4 *hi = reinterpret_cast<float4 *>(a_st + (size_t)s * 2 * A_TILE + cw * 4096) + lane;
-        float4 *lo = reinterpret_cast<float4 *>(a_st + (size_t)s * 2 * A_TILE + A_TILE + cw * 4096) + lane;
+        const int rs = ks % RS, as = ks % AS;
+        mbar_wait(&raw_full[rs], (ks / RS) & 1, 6);
+        const unsigned char *rp = a_raw + (size_t)rs * A_TILE + row * 128;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 x = hi[i * 32];
-          float4 h, l;
-          h.x = __uint_as_float(rna_tf32_bits(x.x)); l.x = __uint_as_float(rna_tf32_bits(x.x - h.x));
-          h.y = __uint_as_float(rna_tf32_bits(x.y)); l.y = __uint_as_float(rna_tf32_bits(x.y - h.y));
-          h.z = __uint_as_float(rna_tf32_bits(x.z)); l.z = __uint_as_float(rna_tf32_bits(x.z - h.z));
-          h.w = __uint_as_float(rna_tf32_bits(x.w)); l.w = __uint_as_float(rna_tf32_bits(x.w - h.w));
-          hi[i * 32] = h;
-          lo[i * 32] = l;
+        for (int c = 0; c < 8; ++c) {      // logical 16-byte chunk c of the row sits at physical chunk c ^ (row & 7)
+          const float4 x = *reinterpret_cast<const float4 *>(rp + ((c ^ (row & 7)) << 4));
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t h = rna_tf32_bits(xs[u]);
+            hi[4 * c + u] = h;
+            lo[4 * c + u] = rna_tf32_bits(xs[u] - __uint_as_float(h));
+          }
         }
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_one(&conv_done[s]);
+        if (lane == 0) mbar_arrive_one(&raw_empty[rs]);     // the raw tile is in registers: its slot may be refilled
+        mbar_wait(&a_empty[as], ((ks / AS) & 1) ^ 1, 7);
+        tc_fence_after();
+        tmem_st32(t_lane + as * 64, hi);
+        tmem_st32(t_lane + as * 64 + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_one(&a_full[as]);
       }
     }
   }
@@ -343,7 +368,7 @@ int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V,
   if (GR > n_row_tiles) GR = n_row_tiles;
   if (GR < 1) GR = 1;
   const unsigned grid = (unsigned)(GR * NCH);
-  const size_t smem = 1024 + (size_t)2 * NKC * NB * KCB + (size_t)SA * 2 * A_TILE + 256;
+  const size_t smem = 1024 + (size_t)2 * NKC * NB * KCB + (size_t)RS * A_TILE + 256;
   MRGCN_REQUIRE(smem <= 227 * 1024, MRGCN_E_NOTSUP, "feat_proj: shared memory (%zu B)", smem);
   MRGCN_PROF("feat_proj");
 #define LAUNCH(NBV)                                                                                                   \
@@ -376,4 +401,16 @@ extern "C" int mrgcn_feat_proj(const float *X, int64_t N, int32_t in_dim, int32_
   MRGCN_REQUIRE(X && weight_F && vt_ws && P, MRGCN_E_BADARG, "feat_proj: null argument");
   return launch_feat_proj(X, N, in_dim, x_stride > 0 ? x_stride : in_dim, weight_F, B, out_dim, vt_ws, xpad_ws, P,
                           (cudaStream_t)stream);
+}
+
+// Host rows (pinned, contiguous [rows][cols] fp32) -> device rows of `pitch` floats (pitch >= cols; the pad columns are not
+// touched: the caller zeroes the buffer once).  Replaces the `.to(device)` of the feature matrix in MRGCN's forward
+// (/root/reference/mrgcn/models/mrgcn.py:203-204) when the features feed the tensor-map loads of mrgcn_feat_proj.
+extern "C" int mrgcn_upload_rows(const float *X_host, int64_t rows, int32_t cols, float *X_dev, int32_t pitch,
+                                 mrgcn_stream_t stream) {
+  MRGCN_REQUIRE(X_host && X_dev && cols > 0 && pitch >= cols && rows >= 0, MRGCN_E_BADARG, "upload_rows: bad arguments");
+  if (rows == 0) return 0;
+  MRGCN_CUDA(cudaMemcpy2DAsync(X_dev, (size_t)pitch * 4, X_host, (size_t)cols * 4, (size_t)cols * 4, (size_t)rows,
+                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
 }

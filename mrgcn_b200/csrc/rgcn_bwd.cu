@@ -752,10 +752,18 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
           // records of the (tile, relation) pieces, then the fixed-order sum per relation
           if (gI->E > 0)
             if (int rc = launch_tab_bwd_c(gI, f.plan, f.weight_I, B, out, a->gact, a->cbuf, st)) return rc;
+          // stage 1: blocks of <= 128 records of one relation; stage 2: the blocks of every relation
+          float *blk = a->cbuf + (size_t)f.plan->n_pieces * B;
+          if (f.plan->n_blks > 0) {
+            MRGCN_PROF("comp_block_reduce");
+            k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)f.plan->n_blks), 256, 0, st>>>(a->cbuf, f.plan->blk_ptr,
+                                                                                                 f.plan->rel_piece_idx,
+                                                                                                 f.plan->n_pieces, B, blk);
+            MRGCN_LAUNCH_CHECK();
+          }
           MRGCN_PROF("comp_reduce");
-          k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)gI->R), 256, 0, st>>>(a->cbuf, f.plan->rel_piece_ptr,
-                                                                                      f.plan->rel_piece_idx, f.plan->n_pieces, B,
-                                                                                      a->g_comp_I);
+          k_seq_reduce<<<dim3((unsigned)cdiv(B, 32), (unsigned)gI->R), 256, 0, st>>>(blk, f.plan->rel_blk_ptr, nullptr,
+                                                                                      f.plan->n_blks, B, a->g_comp_I);
           MRGCN_LAUNCH_CHECK();
         } else {
         if (gI->E > 0) {

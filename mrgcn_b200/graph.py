@@ -67,9 +67,10 @@ def hub_segments(deg, seg):
 TAB_LT = 32          # edges per task of the table-term kernels (csrc/tab.cu)
 TAB_TILE = 480       # a tile starts a new one every TAB_TILE edges of E2: at most TAB_TILE + TAB_LT - 1 edges per tile
 TAB_PIECE = 32       # edges per (tile, relation) piece of the comp-gradient reduction
+TAB_BLOCK = 128      # pieces per block of the two-stage sum of the piece records
 
 
-def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TILE, piece=TAB_PIECE):
+def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TILE, piece=TAB_PIECE, block=TAB_BLOCK):
     """Work plan of the table-term kernels (include/mrgcn_b200.h: mrgcn_tab_plan) from the source-major order E2.
     Pure torch, any device (the CPU tests check its invariants).  colptr: [NS+1], e2_rel: [>=E] integer tensors."""
     dev = colptr.device
@@ -90,8 +91,9 @@ def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TI
     plan = dict(n_tasks=n_tasks, lt=lt, task_src=i32(task_src), task_lo=i32(task_lo), wsrc=i32(wsrc), n_wsrc=len(wsrc))
     if E == 0:
         z = torch.zeros(1, dtype=torch.int32, device=dev)
-        plan.update(n_tiles=0, n_pieces=0, tile_slots=lt, tile_task_ptr=z, tile_e0=z, tperm=z, piece_ptr=z, tile_piece_ptr=z,
-                    rel_piece_ptr=torch.zeros(R + 1, dtype=torch.int32, device=dev), rel_piece_idx=z)
+        zr = torch.zeros(R + 1, dtype=torch.int32, device=dev)
+        plan.update(n_tiles=0, n_pieces=0, n_blks=0, tile_slots=lt, tile_task_ptr=z, tile_e0=z, tperm=z, piece_ptr=z,
+                    tile_piece_ptr=z, rel_piece_ptr=zr, rel_piece_idx=z, blk_ptr=z, rel_blk_ptr=zr)
         return plan
     # tiles: consecutive tasks; a new tile starts whenever a task starts in the next block of `tile` edges
     _, counts = torch.unique_consecutive(task_lo // tile, return_counts=True)
@@ -119,9 +121,17 @@ def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TI
     piece_rel = rel[order][piece_start]
     rel_piece_idx = torch.argsort(piece_rel, stable=True)
     rel_piece_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(torch.bincount(piece_rel, minlength=R), 0)])
-    plan.update(n_tiles=n_tiles, n_pieces=n_pieces, tile_slots=tile_slots, tile_task_ptr=i32(tile_task_ptr), tile_e0=i32(tile_e0),
-                tperm=i32(tperm), piece_ptr=i32(piece_ptr), tile_piece_ptr=i32(tile_piece_ptr), rel_piece_ptr=i32(rel_piece_ptr),
-                rel_piece_idx=i32(rel_piece_idx))
+    # blocks of at most `block` consecutive entries of one relation's piece list (first stage of the record sum)
+    per_rel = rel_piece_ptr[1:] - rel_piece_ptr[:-1]
+    nblk = (per_rel + block - 1) // block
+    rel_blk_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(nblk, 0)])
+    n_blks = int(rel_blk_ptr[-1])
+    blk_rel = torch.repeat_interleave(ar(R), nblk)
+    blk_lo = rel_piece_ptr[blk_rel] + block * (ar(n_blks) - rel_blk_ptr[blk_rel])
+    blk_ptr = torch.cat([blk_lo, torch.tensor([n_pieces], device=dev)])
+    plan.update(n_tiles=n_tiles, n_pieces=n_pieces, n_blks=n_blks, tile_slots=tile_slots, tile_task_ptr=i32(tile_task_ptr),
+                tile_e0=i32(tile_e0), tperm=i32(tperm), piece_ptr=i32(piece_ptr), tile_piece_ptr=i32(tile_piece_ptr),
+                rel_piece_ptr=i32(rel_piece_ptr), rel_piece_idx=i32(rel_piece_idx), blk_ptr=i32(blk_ptr), rel_blk_ptr=i32(rel_blk_ptr))
     return plan
 
 
@@ -264,10 +274,10 @@ class RelGraph:
             with torch.cuda.device(self.device):
                 d = build_tab_plan(self.colptr, self.e2_rel, self.E, self.NS, self.R, LONG_THRESH)
             c = nv.TabPlan()
-            for k in ("n_tasks", "n_wsrc", "n_tiles", "n_pieces", "tile_slots", "lt"):
+            for k in ("n_tasks", "n_wsrc", "n_tiles", "n_pieces", "tile_slots", "lt", "n_blks"):
                 setattr(c, k, int(d[k]))
             for k in ("task_src", "task_lo", "wsrc", "tile_task_ptr", "tile_e0", "tperm", "piece_ptr", "tile_piece_ptr",
-                      "rel_piece_ptr", "rel_piece_idx"):
+                      "rel_piece_ptr", "rel_piece_idx", "blk_ptr", "rel_blk_ptr"):
                 if d[k].numel() == 0:
                     d[k] = torch.zeros(1, dtype=_I32, device=self.device)
                 setattr(c, k, d[k].data_ptr())

@@ -145,7 +145,7 @@ class _LayerFn(torch.autograd.Function):
             if B:
                 g_cI = torch.empty_like(comp_I)
                 if mode & 4:      # records of the (tile, relation) pieces instead of an E x B scratch
-                    cbuf = _empty(plan.n_pieces * B, dev)
+                    cbuf = _empty((plan.n_pieces + plan.n_blks) * B, dev)
                 else:
                     cbuf = _empty(gI.E * B, dev)
                     part_elems = max(part_elems, gI.n_chunks * B)

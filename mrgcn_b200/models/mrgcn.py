@@ -146,10 +146,27 @@ class MRGCN(nn.Module):
         elif not self.rgcn.layers["layer_0"].featureless:
             # extension: pre-computed node features handed over as batch.X[0] (BASELINE.json config 3);
             # the reference has no encoder-free feature path (mrgcn.py:192-207 leaves X_dev = None)
-            X_dev = torch.as_tensor(X).to(rgcn_device, non_blocking=True)
+            X_dev = self._upload_features(torch.as_tensor(X), rgcn_device)
         if X_dev is not None:
             X_dev = X_dev.float()
         return self.rgcn(X_dev, batch.A)
+
+    def _upload_features(self, X, dev):
+        """Host feature matrix -> device, every call (as mrgcn.py:203-204 does), straight into rows of ceil32(in) floats:
+        the layout the projection kernel's tensor-map loads read (csrc/feat_proj.cu), so no padding pass runs on the device.
+        The (zero-padded) device buffer is kept between calls; only the copy is repeated."""
+        if X.is_cuda or X.dim() != 2 or X.dtype != torch.float32 or X.shape[1] < 32 or dev.type != "cuda":
+            return X.to(dev, non_blocking=True)
+        from .. import _native as nv
+        n, d = X.shape
+        pitch = (d + 31) // 32 * 32
+        buf = getattr(self, "_xbuf", None)
+        if buf is None or buf.shape != (n, pitch) or buf.device != torch.empty(0, device=dev).device:
+            buf = self._xbuf = torch.zeros((n, pitch), dtype=torch.float32, device=dev)
+        X = X.contiguous()
+        with torch.cuda.device(dev):
+            nv.check(nv.lib().mrgcn_upload_rows(X.data_ptr(), n, d, buf.data_ptr(), pitch, nv.stream_ptr()), "upload_rows")
+        return buf[:, :d]
 
     def _compute_modality_embeddings(self, F, batch_idx):
         """mrgcn.py:250-305: gate * encoder(data) scattered into the rows of the nodes that carry the modality."""

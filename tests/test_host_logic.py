@@ -133,6 +133,12 @@ def test_tab_plan_invariants_and_reduction_semantics():
         mine = rpi[rpp[r]:rpp[r + 1]]
         assert bool((piece_rel[mine] == r).all())
         assert torch.allclose(rec[mine].sum(0), vals[rel == r].sum(0), atol=1e-9)
+    # two-stage sum: blocks of <= 128 pieces of one relation tile every relation's piece list
+    bp, rbp = p["blk_ptr"].long(), p["rel_blk_ptr"].long()
+    assert int(bp[0]) == 0 and int(bp[-1]) == p["n_pieces"] and int((bp[1:] - bp[:-1]).max()) <= 128 and int(rbp[-1]) == p["n_blks"]
+    for r in range(R):
+        assert int(bp[rbp[r]]) == int(rpp[r]) if rbp[r] < rbp[r + 1] else True
+        assert int(bp[rbp[r + 1]]) == int(rpp[r + 1])
     # an empty graph gives an empty plan
     z = build_tab_plan(torch.zeros(5, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), 0, 4, R, thresh)
     assert z["n_tasks"] == 0 and z["n_tiles"] == 0 and z["n_pieces"] == 0 and z["n_wsrc"] == 4
