@@ -116,11 +116,18 @@ __global__ void k_vcat_split(const float *__restrict__ V, float *__restrict__ vt
 
 // X [N][in] -> Xp [N][KP] (zero padded rows of KP floats: 16-byte multiples, what a tensor map needs)
 __global__ void k_pad_rows(const float *__restrict__ X, float *__restrict__ Xp, int64_t N, int in, int ldx, int KP) {
-  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= N * KP) return;
-  const int64_t j = x / KP;
-  const int k = (int)(x - j * KP);
-  Xp[x] = k < in ? X[j * ldx + k] : 0.f;
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte piece of a padded row
+  const int q = KP / 4;
+  if (x >= N * q) return;
+  const int64_t j = x / q;
+  const int k = 4 * (int)(x - j * q);
+  const float *src = X + j * ldx + k;
+  float4 v;
+  v.x = k < in ? ldg_stream(src) : 0.f;
+  v.y = k + 1 < in ? ldg_stream(src + 1) : 0.f;
+  v.z = k + 2 < in ? ldg_stream(src + 2) : 0.f;
+  v.w = k + 3 < in ? ldg_stream(src + 3) : 0.f;
+  reinterpret_cast<float4 *>(Xp)[x] = v;
 }
 
 template <int NB>
@@ -266,8 +273,11 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             lo[4 * c + u] = rna_tf32_bits(xs[u] - __uint_as_float(h));
           }
         }
+        // The raw tile is in registers: its slot may be refilled.  The refill is an async-proxy (TMA) write after
+        // generic-proxy reads of the same bytes: without the proxy fence the new tile was seen landing under the loads.
+        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_one(&raw_empty[rs]);     // the raw tile is in registers: its slot may be refilled
+        if (lane == 0) mbar_arrive_one(&raw_empty[rs]);
         mbar_wait(&a_empty[as], ((ks / AS) & 1) ^ 1, 7);
         tc_fence_after();
         tmem_st32(t_lane + as * 64, hi);
@@ -353,7 +363,7 @@ int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V,
   if (ldx != KP) {
     MRGCN_REQUIRE(xpad_ws, MRGCN_E_BADARG, "feat_proj: X rows are %d floats apart, need %d (or a padding workspace)", ldx, KP);
     MRGCN_PROF("pad_rows");
-    k_pad_rows<<<(unsigned)cdiv(N * KP, 256), 256, 0, st>>>(X, xpad_ws, N, in, ldx, KP);
+    k_pad_rows<<<(unsigned)cdiv(N * (KP / 4), 256), 256, 0, st>>>(X, xpad_ws, N, in, ldx, KP);
     MRGCN_LAUNCH_CHECK();
     Xp = xpad_ws;
   }

@@ -109,8 +109,7 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
   int2 *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task
   const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_tasks + g.TPW - 1) / g.TPW;
-  const bool writer = g.hs == 0;
-  const bool last_pair = g.op0 == GS - 1;     // (NOP == 1) this lane also zero-fills the row padding
+  const bool writer = g.hs == 0 && g.lane_on;
   for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
     const int t = wi * g.TPW + g.tslot;
     const bool on = g.lane_on && t < n_tasks;
@@ -146,7 +145,13 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
       }
 #pragma unroll
       for (int q = 0; q < NOP; ++q) { acc[q].x += acc1[q].x; acc[q].y += acc1[q].y; }
-      if (HS > 1) {   // partial sums of the base splits, added in split order
+      if (HS == 2) {  // partial sums of the two base splits
+#pragma unroll
+        for (int q = 0; q < NOP; ++q) {
+          acc[q].x += __shfl_down_sync(0xffffffffu, acc[q].x, GS);
+          acc[q].y += __shfl_down_sync(0xffffffffu, acc[q].y, GS);
+        }
+      } else if (HS > 2) {   // ... of more splits, added in split order
 #pragma unroll
         for (int q = 0; q < NOP; ++q) {
           const float2 own = acc[q];
@@ -157,18 +162,11 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
         }
       }
       if (live && writer) {
+        // rows are padded to `ms` floats; the pad columns are never read into a stored sum (agg kernels) and stay unwritten
         const float v = __int_as_float(m.y);
-        // rows are padded to `ms` floats (even, >= out): the pad is written as zeros
 #pragma unroll
-        for (int q = 0; q < NOP; ++q) {
-          const int o = 2 * (g.op0 + 32 * q);
-          if (o < out) *reinterpret_cast<float2 *>(mrow + 64 * q) = make_float2(v * acc[q].x, (EVEN || o + 1 < out) ? v * acc[q].y : 0.f);
-        }
-        if (last_pair || NOP > 1) {
-          const int z0 = 2 * GS - 2 * g.op0;                 // first pad column, relative to this lane's pointer
-          if (NOP == 1) { for (int z = z0; z < ms - 2 * g.op0; z += 2) *reinterpret_cast<float2 *>(mrow + z) = make_float2(0.f, 0.f); }
-          else if (g.op0 == 0) { for (int z = 2 * GS; z < ms; z += 2) *reinterpret_cast<float2 *>(mrow + z) = make_float2(0.f, 0.f); }
-        }
+        for (int q = 0; q < NOP; ++q)
+          if (NOP == 1 || 2 * (g.op0 + 32 * q) < out) *reinterpret_cast<float2 *>(mrow + 64 * q) = make_float2(v * acc[q].x, v * acc[q].y);
       }
     }
   }
@@ -215,23 +213,35 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
       }
       __syncwarp();
       const int nch = min(32, maxlen - c0);
-      for (int s0 = 0; s0 < nch; s0 += 4) {
-        EdgeMeta m[4];
-        float2 t[4][NOP];
+      // groups of U edges; the gathers of group k+1 are in flight while group k is accumulated
+      constexpr int U = (BPT * NOP >= 16) ? 2 : 4;
+      EdgeMeta m[U], mn[U];
+      float2 t[U][NOP], tn[U][NOP];
+      auto fetch = [&](int s0, EdgeMeta (&mm)[U], float2 (&tt)[U][NOP]) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const bool live = s0 + u < mylen;
-          m[u].d = 0; m[u].r = 0; m[u].v = 0.f;
-          if (live) m[u] = tmeta[s0 + u];
-          const float *gp = gact + (size_t)m[u].d * out + 2 * g.op0;
+          mm[u].d = 0; mm[u].r = 0; mm[u].v = 0.f;
+          if (live) mm[u] = tmeta[s0 + u];
+          const float *gp = gact + (size_t)mm[u].d * out + 2 * g.op0;
 #pragma unroll
           for (int q = 0; q < NOP; ++q) {
             const int o = 2 * (g.op0 + 32 * q);
-            t[u][q] = (live && o < out) ? ld2<EVEN>(gp + 64 * q, o + 1 < out) : make_float2(0.f, 0.f);
+            tt[u][q] = (live && o < out) ? ld2<EVEN>(gp + 64 * q, o + 1 < out) : make_float2(0.f, 0.f);
           }
         }
+      };
+      fetch(0, mn, tn);
+      for (int s0 = 0; s0 < nch; s0 += U) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
+          m[u] = mn[u];
+#pragma unroll
+          for (int q = 0; q < NOP; ++q) t[u][q] = tn[u][q];
+        }
+        if (s0 + U < nch) fetch(s0 + U, mn, tn);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
           const float *cr = cbase + m[u].r * CSP;
 #pragma unroll
           for (int q = 0; q < NOP; ++q) { t[u][q].x *= m[u].v; t[u][q].y *= m[u].v; }
@@ -276,8 +286,11 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kCThreads = 128;   // comp-gradient kernel: small CTAs, four per SM, so that a CTA waiting at its tile barrier
+constexpr int kCWarps = kCThreads / 32;   // leaves the SM to the others
+
 template <int BC, int OP, bool EVEN>
-__global__ void __launch_bounds__(kTabThreads, 2)
+__global__ void __launch_bounds__(kCThreads, 4)
 k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
             const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
             const int32_t *__restrict__ tile_task_ptr, const int32_t *__restrict__ tile_e0, int n_tiles,
@@ -296,7 +309,7 @@ k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int e0 = tile_e0[tile], t_lo = tile_task_ptr[tile], t_hi = tile_task_ptr[tile + 1];
     const int n_items = (t_hi - t_lo + TPW - 1) / TPW;
-    for (int wi = warp; wi < n_items; wi += kTabWarps) {
+    for (int wi = warp; wi < n_items; wi += kCWarps) {
       const int t = t_lo + wi * TPW + tslot;
       const bool on = lane_on && t < t_hi;
       int j = 0, lo = 0, len = 0;
@@ -362,7 +375,7 @@ k_tab_bwd_c(const float *__restrict__ TI, int BI, int64_t NS, int out, const int
     __syncthreads();
     // per-relation pieces of the tile, summed in the precomputed order
     const int p_lo = tile_piece_ptr[tile], p_hi = tile_piece_ptr[tile + 1];
-    for (int x = threadIdx.x; x < (p_hi - p_lo) * BI; x += kTabThreads) {
+    for (int x = threadIdx.x; x < (p_hi - p_lo) * BI; x += kCThreads) {
       const int pc = p_lo + x / BI, b = x - (pc - p_lo) * BI;
       const int q_lo = piece_ptr[pc], q_hi = piece_ptr[pc + 1];
       float acc = 0.f;
@@ -379,9 +392,9 @@ static int tab_set_smem(K kernel, size_t bytes) {
   return 0;
 }
 template <class K>
-static unsigned tab_grid(K kernel, size_t smem, int64_t max_ctas) {
+static unsigned tab_grid(K kernel, size_t smem, int64_t max_ctas, int threads = kTabThreads) {
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTabThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int64_t g = (int64_t)kNumSMs * per_sm;
   return (unsigned)(g < max_ctas ? g : (max_ctas > 0 ? max_ctas : 1));
 }
@@ -508,14 +521,14 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
   if (pl->n_tiles == 0) return 0;
   const int LPT = (BI + BC - 1) / BC, TPW = 32 / LPT;
   const int BSP = LPT * BC;
-  const size_t smem = ((size_t)pl->tile_slots * BSP) * 4 + (size_t)kTabWarps * TPW * LT * sizeof(int2);
+  const size_t smem = ((size_t)pl->tile_slots * BSP) * 4 + (size_t)kCWarps * TPW * LT * sizeof(int2);
   MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_bwd_c: tile too large for shared memory (%zu B)", smem);
   MRGCN_PROF("tab_bwd_c");
 #define CALL(BCV, OPV)                                                                                                 \
   do {                                                                                                                 \
     if (int rc = tab_set_smem(k_tab_bwd_c<BCV, OPV, true>, smem)) return rc;                                                 \
-    const unsigned grid = tab_grid(k_tab_bwd_c<BCV, OPV, true>, smem, pl->n_tiles);                                          \
-    k_tab_bwd_c<BCV, OPV, true><<<grid, kTabThreads, smem, st>>>(TI, BI, (int64_t)g->NS, out, g->colptr, pl->task_src,      \
+    const unsigned grid = tab_grid(k_tab_bwd_c<BCV, OPV, true>, smem, pl->n_tiles, kCThreads);                               \
+    k_tab_bwd_c<BCV, OPV, true><<<grid, kCThreads, smem, st>>>(TI, BI, (int64_t)g->NS, out, g->colptr, pl->task_src,      \
                                                            pl->task_lo, pl->tile_task_ptr, pl->tile_e0, pl->n_tiles,   \
                                                            g->e2_dst, g->e2_val, gact, pl->tperm, pl->piece_ptr,       \
                                                            pl->tile_piece_ptr, rec, LPT, BSP, pl->tile_slots);         \

@@ -65,7 +65,7 @@ def hub_segments(deg, seg):
 
 
 TAB_LT = 32          # edges per task of the table-term kernels (csrc/tab.cu)
-TAB_TILE = 480       # a tile starts a new one every TAB_TILE edges of E2: at most TAB_TILE + TAB_LT - 1 edges per tile
+TAB_TILE = 224       # a tile starts a new one every TAB_TILE edges of E2: at most TAB_TILE + TAB_LT - 1 edges per tile
 TAB_PIECE = 32       # edges per (tile, relation) piece of the comp-gradient reduction
 TAB_BLOCK = 128      # pieces per block of the two-stage sum of the piece records
 

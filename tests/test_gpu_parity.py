@@ -434,10 +434,11 @@ def test_ranks_vs_oracle():
         assert np.array_equal(ref, got)     # integer-valued scores: sums are exact in fp32, so ranks are too
 
 
-@pytest.mark.parametrize("N,indim,B,outdim", [(1000, 151, 40, 10), (130, 145, 2, 200), (4097, 64, 8, 16), (257, 32, 3, 16)])
+@pytest.mark.parametrize("N,indim,B,outdim", [(1000, 151, 40, 10), (20011, 151, 40, 10), (130, 145, 2, 200), (40000, 64, 8, 16), (257, 32, 3, 16)])
 def test_feature_projection_tensor_cores(N, indim, B, outdim):
     """mrgcn_feat_proj (tcgen05 + tensor-map TMA, split TF32): P[j, b, :] = X[j, :] . V[b], element-wise against the fp32
-    matmul of the reference's einsum (graph.py:93) with the float64 product adjudicating."""
+    matmul of the reference's einsum (graph.py:93) with the float64 product adjudicating.  The larger cases give every CTA
+    several row tiles (ring wrap-around of the shared-memory and tensor-memory stages)."""
     import ctypes as C
     from mrgcn_b200 import _native as nv
     from mrgcn_b200.layers.graph import padded_features

@@ -111,7 +111,7 @@ def test_tab_plan_invariants_and_reduction_semantics():
     assert int(ttp[0]) == 0 and int(ttp[-1]) == p["n_tasks"] and bool((ttp[1:] > ttp[:-1]).all())
     assert torch.equal(te0, lo[ttp[:-1]])
     tend = torch.cat([te0[1:], torch.tensor([E])])
-    assert int((tend - te0).max()) == p["tile_slots"] <= 480 + lt - 1
+    assert int((tend - te0).max()) == p["tile_slots"] <= 224 + lt - 1
     # pieces: tperm restricted to a tile is a permutation of its slots; a piece has one relation and <= 32 edges
     tperm, pp, tpp = p["tperm"].long(), p["piece_ptr"].long(), p["tile_piece_ptr"].long()
     assert int(pp[0]) == 0 and int(pp[-1]) == E and int((pp[1:] - pp[:-1]).max()) <= 32 and int(tpp[-1]) == p["n_pieces"]
