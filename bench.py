@@ -1,26 +1,33 @@
 #!/usr/bin/env python
-"""bench.py — R-GCN fwd+bwd edges/s on the AM-shape workload (BASELINE.json metric), 1..8 B200.
+"""bench.py — R-GCN fwd+bwd edges/s on the shapes BASELINE.json names (default: AM), 1..8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--shape am]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--shape am|aifb|aifb_b40|synth|fb15k237|yago3-10+]
 
-A step = one full-batch training step of the configured model WITHOUT the optimizer: forward of the
-2-layer R-GCN (am.toml: 151 -> 10 -> 11, 40 bases, identity + feature terms in layer 0), cross-entropy on
-the labelled nodes, backward to every parameter.  edges = nnz of the stacked adjacency (forward + inverse +
-self-loop blocks).  Prints ONE JSON line (rank 0).
+A step = one full-batch training step of the configured model WITHOUT the optimizer.
+  node classification (am, aifb, synth): forward of the 2-layer R-GCN (am.toml: 151 -> 10 -> 11, 40 bases, identity + feature
+      terms in layer 0), cross-entropy on the labelled nodes, backward to every parameter;
+  link prediction (fb15k237, yago3-10+): 1-layer encoder (h = 200, 2 bases, ReLU) over the full graph, DistMult scores of 500
+      positives + 100 in-batch negatives, BCE, backward (/root/reference/mrgcn/tasks/link_prediction.py:244-326); the line
+      also carries `lp.rank_scores_per_s` for compute_ranks_fast on 500 facts (:593-643).
+edges = nnz of the stacked adjacency (forward + inverse + self-loop blocks).  Prints ONE JSON line (rank 0).
 
   value    : device-resident throughput (features already in HBM), CUDA events, max over ranks; the K timed steps are
              replays of ONE captured CUDA graph of the step (static in full-batch training); --no-graph times eager launches
-  e2e      : the same step through the public module call `MRGCN.forward(batch)` with the feature matrix in
-             pinned HOST memory (copied to the device every step, as the reference's forward does,
-             mrgcn/models/mrgcn.py:203-204) and the loss read back to the host
+  e2e      : the same step through the public module call `MRGCN.forward(batch)` with the feature matrix in pinned HOST
+             memory (copied to the device every step, as the reference's forward does, mrgcn/models/mrgcn.py:203-204) and
+             the loss read back to the host; under torchrun the same call runs the node-partitioned model (every rank
+             uploads only the feature rows it owns)
   roofline : dominant kernel of the step, timed live with CUDA events inside the library (mrgcn_profile_enable) in an
              eager pass of the same K steps, against MEASURED_PEAKS.json; `traffic` = its DRAM bytes per launch from the
              ncu capture recorded in profiles/ncu_traffic.json
-  cpu_baseline / --impl reference : the CPU oracle (the reference's own torch.sparse op sequence,
-             oracle/reference_port.py) on a bounded sample of the same workload, on this box's host cores
+  cpu_baseline / --impl reference : the UNMODIFIED reference modules (vendored by __graft_entry__.build() into the
+             git-ignored baseline/_ref; `kind: "reference"`) - or the oracle port when that install is absent (`kind:
+             "port"`) - on a sample of the same workload sized to the host's free RAM and to a time budget
+  parity_vs_n1 (N > 1): loss and small-parameter gradients of the partitioned step against the single-GPU model with the
+             same weights, computed on rank 0 inside the run (max relative error)
+  collectives (N > 1): name, bytes, calls per step and milliseconds of every collective of the step
 
-N > 1 (torchrun): the graph is 1-D node-partitioned (mrgcn_b200/partition.py); total work is fixed
-("scaling": "strong").
+N > 1 (torchrun): the graph is 1-D node-partitioned (mrgcn_b200/partition.py); total work is fixed ("scaling": "strong").
 """
 import argparse
 import json
@@ -40,6 +47,8 @@ import torch.nn as nn  # noqa: E402
 METRIC = "rgcn_fwd_bwd_edges_per_s"
 UNIT = "edges/s"
 NUM_LABELLED = 10000
+LP_POS = 500          # fb15k-237.toml / yago3-10+.toml: test_batchsize = 500 positives per step, + 20 % negatives
+SURVEY_B_PER_EDGE = {"am": 5012.0, "fb15k237": 4891.0}      # per-edge-gather formulation of the step
 
 
 def peaks():
@@ -49,6 +58,17 @@ def peaks():
             p = json.load(f)
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_ram_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable"):
+                    return int(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 16.0
 
 
 class ClockSampler:
@@ -110,82 +130,168 @@ def labelled_nodes(n, num_classes, seed=1):
     return idx, rng.integers(0, num_classes, size=len(idx))
 
 
-def algorithmic_bytes(g, in0, dims, B, P=1):
-    """Algorithmic bytes per launch of every kernel of one step: 4 B per structure word read,
-    gathered operand rows counted per edge, every output written once.  Returns {kernel: [bytes per launch...]}
-    in launch order (layer 0 fwd, layer 1 fwd, layer 1 bwd, layer 0 bwd)."""
+def lp_batch(tr, seed=1):
+    """One training batch of the LP loop: the first LP_POS triples + in-batch negatives made exactly as
+    link_prediction.py:247-264 does (host NumPy RNG), labels 1 / 0."""
+    from mrgcn_b200.tasks.link_prediction import negative_samples
+    data = tr[:LP_POS].astype(np.int64)
+    corrupted, Y = negative_samples(data, np.random.RandomState(seed))
+    trip = np.concatenate([data, np.asarray(corrupted, dtype=np.int64)], 0)
+    return trip, Y
+
+
+def modules_of(shp):
+    dims = shp.dims
+    if shp.task == "lp":      # link_prediction.py:449-464: ReLU on every layer, the last one included
+        return [(dims[k], dims[k + 1], "mrgcn", nn.ReLU()) for k in range(len(dims) - 1)]
+    return [(dims[k], dims[k + 1], "mrgcn", nn.ReLU() if k + 2 < len(dims) else None) for k in range(len(dims) - 1)]
+
+
+def algorithmic_bytes(g, in0, dims, B, fused):
+    """Algorithmic bytes per launch of the kernels of one step: 4 B per structure word read, table / feature
+    rows counted once per pass where a kernel keeps them on chip and per edge where it gathers them, every output written
+    once.  Returns {kernel: [bytes per launch...]} in launch order.  g: sizes of the (rank's) graph and work plan."""
     E, ND, NS, R = g["E"], g["ND"], g["NS"], g["R"]
-    nch = g["n_chunks"]
-    h, c = dims
+    nch, ntask, npc, nblk = g["n_chunks"], g.get("n_tasks", 0), g.get("n_pieces", 0), g.get("n_blks", 0)
+    h = dims[0]
+    c = dims[1] if len(dims) > 1 else None
+    kp = (in0 + 31) // 32 * 32
     out = {}
     ms = lambda d: 4 if d <= 4 else 8 if d <= 8 else (d + 15) // 16 * 16      # padded message row (mrgcn_msg_stride)
 
     def add(k, v):
         out.setdefault(k, []).append(float(v))
-    # ---- layer 0 forward (identity + feature)
-    add("ident_msg_fwd", B * NS * h * 4 + E * 12 + NS * 4 + E * ms(h) * 4 + R * B * 4)
-    add("basis_mix_fwd", B * in0 * h * 4 + R * B * 4 + R * in0 * h * 4)
-    add("feat_msg_fwd", E * (8 + in0 * 4) + R * in0 * h * 4 + E * ms(h) * 4)
-    add("agg_fwd", ND * 4 + E * 2 * (4 + ms(h) * 4) + ND * h * 4)
-    # ---- layer 1 forward (feature only)
-    add("basis_mix_fwd", B * h * c * 4 + R * B * 4 + R * h * c * 4)
-    add("feat_msg_fwd", E * (8 + h * 4) + R * h * c * 4 + E * ms(c) * 4)
-    add("agg_fwd", ND * 4 + E * (4 + ms(c) * 4) + ND * c * 4)
-    # ---- layer 1 backward
-    add("act_bwd", 2 * ND * c * 4)
-    add("feat_bwd_w", E * (12 + h * 4 + c * 4) + nch * h * c * 4)
-    add("feat_w_reduce", nch * h * c * 4 + R * h * c * 4)
-    add("basis_mix_bwd_v", R * h * c * 4 + B * h * c * 4)
-    add("basis_mix_bwd_c", R * h * c * 4 + B * h * c * 4 + R * B * 4)
-    add("feat_bwd_x_msg", E * (8 + c * 4) + R * h * c * 4 + E * ms(h) * 4)
-    add("feat_bwd_x_agg", NS * 4 + E * (4 + ms(h) * 4) + NS * h * 4)
-    # ---- layer 0 backward
+    Bn = max(B, 0)
+    if Bn:
+        if fused:
+            add("vcat_split", Bn * in0 * h * 4 + 2 * Bn * h * kp * 4)
+            add("feat_proj", NS * kp * 4 + NS * Bn * h * 4 + 2 * Bn * h * kp * 4)
+        add("tab_msg_fwd", Bn * NS * h * 4 * (2 if fused else 1) + E * 8 + ntask * 8 + NS * 4 + E * h * 4 + R * Bn * 4 * (2 if fused else 1))
+        add("tab_bwd_w", E * (12 + h * 4) + NS * 8 + Bn * NS * h * 4 + R * Bn * 4)
+        add("tab_bwd_c", Bn * NS * h * 4 + E * (8 + h * 4) + ntask * 8 + E * 4 + npc * (4 + Bn * 4))
+        add("comp_block_reduce", npc * (4 + Bn * 4) + nblk * Bn * 4)
+        add("comp_reduce", nblk * Bn * 4 + R * Bn * 4)
+    if in0 and not fused:
+        add("feat_msg_fwd", E * (8 + in0 * 4) + R * in0 * h * 4 + E * ms(h) * 4)
+    n_msgs0 = (1 if Bn else 0) + (1 if (in0 and not fused) else 0)
+    add("agg_fwd", ND * 4 + E * n_msgs0 * (4 + ms(h) * 4) + (E * (12 + h * 4) if not Bn else 0) + ND * h * 4)
+    if in0:
+        add("feat_bwd_w", E * (12 + in0 * 4 + h * 4) + nch * in0 * h * 4)
+        add("feat_w_reduce", nch * in0 * h * 4 + R * in0 * h * 4)
     add("act_bwd", 3 * ND * h * 4)
-    add("ident_bwd_w", E * (12 + h * 4) + NS * 4 + B * NS * h * 4 + R * B * 4)
-    add("ident_bwd_c", B * NS * h * 4 + E * (12 + h * 4) + NS * 4 + E * B * 4)
-    add("comp_chunk_reduce", E * (4 + B * 4) + nch * B * 4)
-    add("comp_reduce", nch * B * 4 + R * B * 4)
-    add("feat_bwd_w", E * (12 + in0 * 4 + h * 4) + nch * in0 * h * 4)
-    add("feat_w_reduce", nch * in0 * h * 4 + R * in0 * h * 4)
-    add("basis_mix_bwd_v", R * in0 * h * 4 + B * in0 * h * 4)
-    add("basis_mix_bwd_c", R * in0 * h * 4 + B * in0 * h * 4 + R * B * 4)
+    if c is not None:
+        add("feat_msg_fwd", E * (8 + h * 4) + R * h * c * 4 + E * ms(c) * 4)
+        add("agg_fwd", ND * 4 + E * (4 + ms(c) * 4) + ND * c * 4)
+        add("act_bwd", 2 * ND * c * 4)
+        add("feat_bwd_w", E * (12 + h * 4 + c * 4) + nch * h * c * 4)
+        add("feat_w_reduce", nch * h * c * 4 + R * h * c * 4)
+        add("feat_bwd_x_msg", E * (8 + c * 4) + R * h * c * 4 + E * ms(h) * 4)
+        add("feat_bwd_x_agg", NS * 4 + E * (4 + ms(h) * 4) + NS * h * 4)
     return out
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_step(shape_name, sample_scale, steps, warmup, threads):
-    """The reference's CPU path (oracle port: same scipy/torch-CPU calls, oracle/reference_port.py) on a bounded
-    sample of the workload: N and triples scaled by `sample_scale`, R / bases / dims unchanged."""
+def _reference_modules():
+    """The unmodified reference (baseline/_ref, installed by __graft_entry__.build()) with the import-only rdflib stand-in
+    of tests/golden/_stubs; None when the install is absent."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "mrgcn")):
+        return None
+    for p in (os.path.join(ROOT, "tests", "golden", "_stubs"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        from mrgcn.models.rgcn import RGCN
+        from mrgcn.tasks import link_prediction as lp
+        return RGCN, lp
+    except Exception as exc:      # pragma: no cover
+        print("bench: reference import failed (%s); using the oracle port" % exc, file=sys.stderr)
+        return None
+
+
+def cpu_reference_step(shape_name, scale, steps, warmup, threads):
+    """One training step (no optimizer) of the reference's CPU path on the workload scaled by `scale` (N and triples
+    together; R, bases and layer widths unchanged).  Returns (nnz, [seconds per step], N, kind)."""
     from oracle import reference_port as rp
     torch.set_num_threads(threads)
-    shp, n, tr = make_workload(shape_name, sample_scale)
-    R = shp.num_relations
-    A = rp.csr_to_coo(rp.as_float32(rp.stacked_adjacency(tr, n, shp.num_props)), torch.int8 if False else torch.float32)
-    nnz = A._nnz()
+    shp, n, tr = make_workload(shape_name, scale)
+    R, B = shp.num_relations, shp.num_bases if shp.num_bases > 0 else -1
     dims = shp.dims
+    fl = dims[0] == 0
+    A = rp.csr_to_coo(rp.as_float32(rp.stacked_adjacency(tr, n, shp.num_props)), torch.float32)
+    nnz = A._nnz()
+    mods = modules_of(shp)
+    ref = _reference_modules()
     torch.manual_seed(1)
-    modules = [(dims[k], dims[k + 1], "mrgcn", "relu" if k + 2 < len(dims) else None) for k in range(len(dims) - 1)]
-    layers, _ = rp.init_rgcn_params(modules, R, n, shp.num_bases if shp.num_bases > 0 else -1, dims[0] == 0, False, False)
-    for l in layers:
-        for v in l.values():
+    X = torch.randn(n, dims[0]) if not fl else None
+    if shp.task == "nc":
+        idx, y = labelled_nodes(n, dims[-1])
+        idx, y = torch.from_numpy(idx), torch.from_numpy(y)
+    else:
+        trip, Y = lp_batch(tr)
+        trip = torch.from_numpy(trip)
+    if ref is not None:
+        RefRGCN, ref_lp = ref
+        model = RefRGCN(mods, R, n, B, 0.0, fl, False, shp.task == "lp")
+        params = list(model.parameters())
+
+        def step():
+            for p in params:
+                p.grad = None
+            out = model(X, A)
+            if shp.task == "nc":
+                loss = nn.functional.cross_entropy(out[idx], y)
+            else:
+                sc = ref_lp.score_distmult_bc((trip[:, 0], trip[:, 1], trip[:, 2]), out, model.relations)
+                loss = nn.functional.binary_cross_entropy_with_logits(sc, Y)
+            loss.backward()
+        kind = "reference"
+    else:
+        layers, rel = rp.init_rgcn_params(mods, R, n, B, fl, False, shp.task == "lp")
+        acts = ["relu" if m[3] is not None else None for m in mods]
+        params = [v for l in layers for v in l.values()] + ([rel] if rel is not None else [])
+        for v in params:
             v.requires_grad_(True)
-    X = torch.randn(n, dims[0]) if dims[0] > 0 else None
-    idx, y = labelled_nodes(n, dims[-1])
-    idx, y = torch.from_numpy(idx), torch.from_numpy(y)
+
+        def step():
+            for p in params:
+                p.grad = None
+            out = rp.rgcn_forward(layers, acts, X, A, num_nodes=n, num_relations=R, num_bases=B, featureless=fl)
+            if shp.task == "nc":
+                loss = rp.nc_loss(out, idx, y)
+            else:
+                loss = rp.lp_loss(rp.distmult_score((trip[:, 0], trip[:, 1], trip[:, 2]), out, rel), Y)
+            loss.backward()
+        kind = "port"
     times = []
     for it in range(warmup + steps):
-        for l in layers:
-            for v in l.values():
-                v.grad = None
         t0 = time.perf_counter()
-        out = rp.rgcn_forward(layers, [m[3] for m in modules], X, A, num_nodes=n, num_relations=R,
-                              num_bases=shp.num_bases if shp.num_bases > 0 else -1, featureless=dims[0] == 0)
-        loss = rp.nc_loss(out, idx, y)
-        loss.backward()
-        dt = time.perf_counter() - t0
+        step()
         if it >= warmup:
-            times.append(dt)
-    return nnz, times, n
+            times.append(time.perf_counter() - t0)
+    return nnz, times, n, kind
+
+
+def pick_cpu_scale(shape_name, budget_s, steps, threads):
+    """Largest power-of-two fraction of the workload whose reference step fits the host (free RAM: the reference holds
+    ~7 tensors of R*N*out floats, measured 4.2 GB at AM/16) and the time budget (cost is ~linear in N: calibrated with
+    one step at a small scale)."""
+    from mrgcn_b200.synth import SHAPES
+    shp = SHAPES[shape_name]
+    free = host_ram_gb()
+    copies = 7 if shp.task == "nc" else 4
+    probe = 1.0 / 64 if shp.num_nodes > 100000 else 1.0 / 8
+    nnz, times, _, _ = cpu_reference_step(shape_name, probe, 1, 1, threads)
+    rate = nnz / times[0]                                    # edges/s at the probe scale
+    full_nnz = shp.nnz
+    scale = 1.0
+    while scale > probe:
+        need_gb = copies * 4e-9 * shp.num_relations * shp.num_nodes * scale * max(shp.dims[1:])
+        t_est = full_nnz * scale / rate * (steps + 1)
+        if need_gb < 0.6 * free and t_est < budget_s:
+            break
+        scale /= 2
+    return max(scale, probe), free
 
 
 def run_reference(args):
@@ -193,16 +299,20 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    scale = args.cpu_sample_scale
-    nnz, times, n = cpu_reference_step(args.shape, scale, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
+    steps = max(1, min(args.steps, 3))
+    warm = 1
+    scale, free = (args.cpu_sample_scale, host_ram_gb()) if args.cpu_sample_scale else pick_cpu_scale(args.shape, 150.0, steps, threads)
+    scale *= args.scale
+    nnz, times, n, kind = cpu_reference_step(args.shape, scale, steps, warm, threads)
     ms = 1e3 * float(np.mean(times))
     val = nnz / (ms / 1e3)
-    sample = "%s-shape scaled x%g (N=%d, nnz=%d; R, bases, dims unchanged), %d timed step(s)" % (args.shape, scale, n, nnz, len(times))
+    sample = ("%s-shape scaled x%g (N=%d, nnz=%d; R, bases, dims unchanged), 1 warm-up + %d timed step(s), host RAM free %.0f GB"
+              % (args.shape, scale, n, nnz, len(times), free))
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(times),
-            "warmup": max(0, min(args.warmup, 1)), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.shape), "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -211,6 +321,11 @@ def run_reference(args):
 def workload_name(shape):
     from mrgcn_b200.synth import SHAPES
     s = SHAPES[shape]
+    if s.task == "lp":
+        return ("%s-shape link prediction: N=%d, R=%d, nnz=%d (synthetic power-law graph), R-GCN encoder %s (ReLU), %d bases, "
+                "full batch, DistMult on %d positives + %d negatives, BCE" % (shape.upper(), s.num_nodes, s.num_relations, s.nnz,
+                                                                              "->".join(str(d) for d in s.dims), s.num_bases,
+                                                                              LP_POS, LP_POS // 5))
     return ("%s-shape node classification: N=%d, R=%d, nnz=%d (synthetic power-law graph), R-GCN %s, %d bases, "
             "full batch, CE on %d labelled nodes" % (shape.upper(), s.num_nodes, s.num_relations, s.nnz,
                                                      "->".join(str(d) for d in s.dims), s.num_bases, NUM_LABELLED))
@@ -225,9 +340,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shape", default="am")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and triples together (debug)")
-    ap.add_argument("--cpu-sample-scale", type=float, default=1.0 / 16)
+    ap.add_argument("--cpu-sample-scale", type=float, default=0.0, help="0 = sized to host RAM and a time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N>1 vs N=1 parity figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -235,10 +351,13 @@ def main():
 
     import torch.distributed as dist
     from mrgcn_b200 import _native as nv
+    from mrgcn_b200 import partition as part
     from mrgcn_b200.graph import RelGraph
     from mrgcn_b200.data.batch import FullBatch
+    from mrgcn_b200.layers.graph import fused_projection_pitch, padded_features
     from mrgcn_b200.models.mrgcn import MRGCN
-    from mrgcn_b200.partition import PartitionedRGCN, balanced_bounds, node_weights
+    from mrgcn_b200.models.rgcn import RGCN
+    from mrgcn_b200.tasks.link_prediction import compute_ranks_fast, score_distmult_bc
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,80 +375,142 @@ def main():
     R, B = shp.num_relations, shp.num_bases if shp.num_bases > 0 else -1
     dims = shp.dims
     featureless = dims[0] == 0
-    modules = [(dims[k], dims[k + 1], "mrgcn", nn.ReLU() if k + 2 < len(dims) else None) for k in range(len(dims) - 1)]
+    is_lp = shp.task == "lp"
+    modules = modules_of(shp)
     full = RelGraph.from_triples(tr, N, shp.num_props, device=dev)
     nnz = full.E
-    lab_idx, lab_y = labelled_nodes(N, dims[-1])
-    torch.manual_seed(1 + rank)
+    fused = bool(not featureless and fused_projection_pitch(dims[0], B, dims[1]))
     Xh = None
     if not featureless:
         Xh = torch.empty((N, dims[0]), dtype=torch.float32).pin_memory()
-        g = torch.Generator().manual_seed(1)       # identical features on every rank
-        Xh.normal_(generator=g)
-    # device-resident features live in rows of ceil32(in) floats (what the projection kernel's tensor-map loads read);
-    # the e2e path uploads into the same layout every step (MRGCN._upload_features)
-    from mrgcn_b200.layers.graph import padded_features
-    Xd = padded_features(Xh.to(dev)) if Xh is not None else None
+        Xh.normal_(generator=torch.Generator().manual_seed(1))      # identical features on every rank
     ce = nn.CrossEntropyLoss(reduction="sum")
-
-    if world == 1:
-        model = MRGCN(modules, [], R, N, num_bases=B, p_dropout=0.0, featureless=featureless, bias=False)
-        model.to(dev)
-        graph = full
-        idx_d, y_d = torch.from_numpy(lab_idx).to(dev), torch.from_numpy(lab_y).to(dev)
+    bce = nn.BCEWithLogitsLoss(reduction="sum")
+    if is_lp:
+        trip_np, Yh = lp_batch(tr)
+        n_lab = len(trip_np)
+    else:
+        lab_idx, lab_y = labelled_nodes(N, dims[-1])
         n_lab = len(lab_idx)
-        params = list(model.parameters())
+
+    # the model, built through the drop-in class: under torchrun it is node-partitioned (equal node ranges)
+    torch.manual_seed(1)
+    model = MRGCN(modules, [], R, N, num_bases=B, p_dropout=0.0, featureless=featureless, bias=False, link_prediction=is_lp)
+    model.to(dev)
+    rg = model.rgcn
+    params = list(model.parameters())
+    row, col, val = full.coo
+    A_coo = torch.sparse_coo_tensor(torch.stack([row, col]), val, (N, R * N))      # what the reference's batch carries
+    batch = FullBatch(full if world == 1 else A_coo, [Xh if Xh is not None else torch.empty((N, 0))], np.arange(N))
+
+    parity = None
+    if world == 1:
+        graph = full
+        Xd = padded_features(Xh.to(dev)) if Xh is not None else None      # rows of ceil32(in) floats (tensor-map loads)
+        if is_lp:
+            trip_d, Y_d = torch.from_numpy(trip_np).to(dev), Yh.to(dev)
+        else:
+            idx_d, y_d = torch.from_numpy(lab_idx).to(dev), torch.from_numpy(lab_y).to(dev)
+
+        def loss_of(out):
+            if is_lp:
+                return bce(score_distmult_bc((trip_d[:, 0], trip_d[:, 1], trip_d[:, 2]), out, rg.relations), Y_d) / n_lab
+            return ce(out[idx_d], y_d) / n_lab
 
         def step_device():
             for p in params:
                 p.grad = None
-            out = model.rgcn(Xd, graph)
-            loss = ce(out[idx_d], y_d) / n_lab
+            loss = loss_of(rg(Xd, graph))
             loss.backward()
             return loss
-
-        batch = FullBatch(graph, [Xh if Xh is not None else torch.empty((N, 0))], np.arange(N))
 
         def step_e2e():
             for p in params:
                 p.grad = None
-            out = model(batch)                         # host features -> device inside the call
-            loss = ce(out[idx_d], y_d) / n_lab
+            loss = loss_of(model(batch))                # host features -> device inside the call
             loss.backward()
-            return float(loss.item())                  # device -> host read of the step's result
+            return float(loss.item())                   # device -> host read of the step's result
         g_meta = dict(E=full.E, ND=full.ND, NS=full.NS, R=R, n_chunks=full.n_chunks)
+        plan = full._tab[1] if getattr(full, "_tab", None) else None
     else:
-        row, col, val = full.coo
-        bounds = balanced_bounds(node_weights(row, col, N), world)
-        model = PartitionedRGCN(modules, R, N, B, featureless, False, False, bounds, rank)
-        model.to(dev)
-        model.set_graph(row, col, val)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        m = (lab_idx >= lo) & (lab_idx < hi)
-        idx_d, y_d = torch.from_numpy(lab_idx[m] - lo).to(dev), torch.from_numpy(lab_y[m]).to(dev)
-        n_lab = len(lab_idx)
-        params = list(model.parameters())
-        del full, row, col, val
-        torch.cuda.empty_cache()
+        lay = rg.lay
+        lo, hi = lay.lo, lay.hi
+        # ---- N > 1 vs N = 1: the same weights on one GPU (rank 0), loss and small-parameter gradients compared
+        ref_state = None
+        if not args.no_parity:
+            torch.manual_seed(1)
+            ref = RGCN(modules, R, N, B, 0.0, featureless, False, is_lp)      # identical on every rank (same seed)
+            ref_state = {k: v.clone() for k, v in ref.state_dict().items()}
+            rg.load_full_state(ref_state)
+        rg.to(dev)
+        rg.set_graph(row, col, val)
+        model._part_A = A_coo
+        src_part = rg.layer0_is_source_partitioned()
+        Xd = None
+        if Xh is not None:
+            Xd = padded_features(Xh[lo:hi].to(dev)) if src_part else lay.to_padded(Xh.to(dev))
+        if is_lp:
+            mine = np.arange(n_lab) % world == rank                         # the rank's shard of the batch's triples
+            t_own = torch.from_numpy(trip_np[mine]).to(dev)
+            trip_d = torch.stack([lay.pad_ids(t_own[:, 0]), t_own[:, 1], lay.pad_ids(t_own[:, 2])], 1)
+            Y_d = Yh[torch.from_numpy(mine)].to(dev)
+        else:
+            m = (lab_idx >= lo) & (lab_idx < hi)
+            idx_d, y_d = torch.from_numpy(lab_idx[m] - lo).to(dev), torch.from_numpy(lab_y[m]).to(dev)
+            idx_all, y_all = torch.from_numpy(lab_idx).to(dev), torch.from_numpy(lab_y).to(dev)
 
-        def step_device(X=None):
+        def step_device():
+            rg.hooks_enabled = False
             for p in params:
                 p.grad = None
-            out = model(Xd if X is None else X)
-            loss = ce(out[idx_d], y_d) / n_lab
+            H = rg(Xd)                                                       # the rank's rows
+            if is_lp:      # all-gather E once, score the rank's shard of the triples, reduce-scatter dE in backward
+                E_all = part.GatherRows.apply(H, lay)
+                loss = bce(score_distmult_bc((trip_d[:, 0], trip_d[:, 1], trip_d[:, 2]), E_all, rg.relations), Y_d) / n_lab
+            else:
+                loss = ce(H[idx_d], y_d) / n_lab
             loss.backward()
-            model.sync_grads()
+            rg.sync_grads()
             return loss
 
-        from mrgcn_b200.partition import gather_rows
-
         def step_e2e():
-            # every rank copies only the rows it owns from pinned host memory; NVLink all-gather rebuilds the matrix
-            Xfull = gather_rows(Xh[lo:hi].to(dev, non_blocking=True), model.lay) if Xh is not None else None
-            loss = step_device(Xfull)
-            dist.all_reduce(loss)
+            rg.hooks_enabled = True                       # the drop-in path: gradients of replicated weights all-reduced by hooks
+            for p in params:
+                p.grad = None
+            out = model(batch)                            # every rank uploads the feature rows it owns; logits of all nodes
+            if is_lp:
+                t = torch.from_numpy(trip_np).to(dev)
+                loss = bce(score_distmult_bc((t[:, 0], t[:, 1], t[:, 2]), out, rg.relations), Yh.to(dev)) / n_lab
+            else:
+                loss = ce(out[idx_all], y_all) / n_lab
+            loss.backward()
             return float(loss.item())
-        g_meta = dict(E=model.gF.E, ND=model.gF.ND, NS=model.gF.NS, R=R, n_chunks=model.gF.n_chunks)
+        if ref_state is not None:
+            loss_p = step_device().detach().clone()
+            dist.all_reduce(loss_p)
+            small = {n: p.grad.clone() for n, p in rg.named_parameters() if n != "layers.layer_0.weight_I" and p.grad is not None}
+            if rank == 0:
+                ref.to(dev)
+                Xr = padded_features(Xh.to(dev)) if Xh is not None else None
+                out = ref(Xr, full)
+                if is_lp:
+                    t = torch.from_numpy(trip_np).to(dev)
+                    lr = bce(score_distmult_bc((t[:, 0], t[:, 1], t[:, 2]), out, ref.relations), Yh.to(dev)) / n_lab
+                else:
+                    lr = ce(out[torch.from_numpy(lab_idx).to(dev)], torch.from_numpy(lab_y).to(dev)) / n_lab
+                lr.backward()
+                errs = {"loss": abs(float(loss_p) - float(lr)) / max(abs(float(lr)), 1e-30)}
+                for n, p in ref.named_parameters():
+                    if n in small:
+                        errs[n] = float((small[n] - p.grad).abs().max()) / max(float(p.grad.abs().max()), 1e-30)
+                parity = {"max_rel_err": max(errs.values()), "per_tensor": errs, "loss_n1": float(lr), "loss": float(loss_p)}
+                del ref, out, Xr
+            del ref_state
+            torch.cuda.empty_cache()
+        g_meta = dict(E=rg.gI.E, ND=rg.gI.ND, NS=rg.gI.NS, R=R, n_chunks=rg.gI.n_chunks)
+        plan = rg.gI._tab[1] if getattr(rg.gI, "_tab", None) else None
+        del full
+        torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
@@ -366,6 +547,46 @@ def main():
     # eager pass: per-kernel CUDA-event profile (kernel table, roofline) and the launch count
     _, _, launches, prof = timed(step_device, args.steps, args.warmup, profile=True)
     launches_per_step = launches / max(args.steps, 1)
+    if plan is None:
+        g_ = full if world == 1 else rg.gI
+        plan = g_._tab[1] if getattr(g_, "_tab", None) else None
+    if plan is not None:
+        g_meta.update(n_tasks=plan["n_tasks"], n_pieces=plan["n_pieces"], n_blks=plan["n_blks"])
+
+    # collectives of one step (N > 1): sizes from the partition's log, each timed on its own
+    collectives = None
+    if world > 1:
+        part.COMM_LOG = []
+        step_device()
+        torch.cuda.synchronize()
+        log, part.COMM_LOG = part.COMM_LOG, None
+        collectives = []
+        for name in ("reduce_scatter", "all_gather", "all_reduce"):
+            sizes = [b for n_, b in log if n_ == name]
+            if not sizes:
+                continue
+            nbytes = max(sizes)
+            buf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            piece = torch.empty(max(nbytes // 4 // world, 1), dtype=torch.float32, device=dev)
+
+            def run():
+                if name == "reduce_scatter":
+                    dist.reduce_scatter_tensor(piece, buf[:piece.numel() * world])
+                elif name == "all_gather":
+                    dist.all_gather_into_tensor(buf[:piece.numel() * world], piece)
+                else:
+                    dist.all_reduce(buf)
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                run()
+            b.record()
+            torch.cuda.synchronize()
+            collectives.append({"name": name, "bytes": int(nbytes), "calls_per_step": len(sizes), "ms_per_call": a.elapsed_time(b) / 10})
+
     # timed pass: the same step captured once into a CUDA graph and replayed (the step is static in full-batch
     # training: same graph, same shapes, same buffers every epoch), which removes the host launch overhead that
     # dominates once the partitioned step drops to a few ms.  Falls back to eager launches if capture fails.
@@ -399,6 +620,26 @@ def main():
     ms_e2e, wall_e2e, _, _ = timed(step_e2e, e_steps, 2)
     ms_e2e_step = max(ms_e2e, wall_e2e) / e_steps
     h2d = int(Xh.numel() * 4) if Xh is not None else 0      # whole job: the N ranks together copy the matrix once
+    if is_lp:
+        h2d += int(trip_np.nbytes + Yh.numel() * 4)
+
+    # ranking throughput (LP shapes, 1 GPU): compute_ranks_fast on one test batch, raw and filtered
+    lp_extra = None
+    if is_lp and world == 1:
+        with torch.no_grad():
+            emb = rg(Xd, graph).detach()
+            facts = torch.from_numpy(tr[:LP_POS].astype(np.int64))
+            lp_extra = {}
+            for flt in (False, True):
+                compute_ranks_fast(facts, emb, rg.relations, 50, flt)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    compute_ranks_fast(facts, emb, rg.relations, 50, flt)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / 3
+                lp_extra["filtered" if flt else "raw"] = {"facts": LP_POS, "candidates": N, "ms": dt * 1e3,
+                                                           "rank_scores_per_s": 2 * LP_POS * N / dt}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -406,7 +647,7 @@ def main():
         kernels = {}
         if prof:
             # per-kernel table; the dominant kernel (largest share of the step) is the one reported
-            alg = algorithmic_bytes(g_meta, dims[0], dims[1:], max(B, 0)) if (len(dims) == 3 and not featureless and B > 0) else {}
+            alg = algorithmic_bytes(g_meta, dims[0], dims[1:], max(B, 0), fused)
             tot = sum(v[1] for v in prof.values())
             for name, (n, ms) in prof.items():
                 per_step = n // args.steps if args.steps else n
@@ -424,29 +665,42 @@ def main():
                 if t and k["launches_per_step"]:
                     traffic = t["bytes_per_step"] / k["launches_per_step"]      # per launch, like `achieved`
             if k["gbps"]:
+                step_gb = sum(v["alg_gb_per_step"] or 0 for v in kernels.values())
                 roof = {"kernel": top, "bound": "hbm", "achieved": k["gbps"], "peak": peak, "unit": "GB/s",
                         "frac": k["gbps"] / peak, "traffic": traffic, "peak_source": peak_src,
                         "alg_bytes_per_launch": k["alg_gb_per_step"] * 1e9 / max(k["launches_per_step"], 1),
                         "launches_per_step": k["launches_per_step"], "ms_per_step": k["ms_per_step"], "share_of_step": k["share"],
-                        "step_alg_gb": sum(v["alg_gb_per_step"] or 0 for v in kernels.values()),
-                        "step_gbps": sum(v["alg_gb_per_step"] or 0 for v in kernels.values()) / (ms_step / 1e3)}
+                        "step_alg_gb": step_gb, "step_gbps": step_gb / (ms_step / 1e3), "step_frac": step_gb / (ms_step / 1e3) / peak}
+                if args.shape in SURVEY_B_PER_EDGE and world == 1 and args.scale == 1.0:
+                    sgb = SURVEY_B_PER_EDGE[args.shape] * nnz / 1e9      # the survey's per-edge-gather formulation of the same step
+                    roof.update(survey_step_gb=sgb, survey_step_frac=sgb / (ms_step / 1e3) / peak)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cnnz, times, cn = cpu_reference_step(args.shape, args.cpu_sample_scale * args.scale, 2, 1, threads)
-            cpu = {"value": cnnz / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "%s-shape scaled x%g (N=%d, nnz=%d; R, bases, dims unchanged), 1 warm-up + 2 timed steps" % (
-                       args.shape, args.cpu_sample_scale * args.scale, cn, cnnz)}
+            cscale, free = (args.cpu_sample_scale, host_ram_gb()) if args.cpu_sample_scale else pick_cpu_scale(args.shape, 25.0, 2, threads)
+            cnnz, times, cn, kind = cpu_reference_step(args.shape, cscale * args.scale, 2, 1, threads)
+            cpu = {"value": cnnz / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": "%s-shape scaled x%g (N=%d, nnz=%d; R, bases, dims unchanged), 1 warm-up + 2 timed steps, host RAM free %.0f GB" % (
+                       args.shape, cscale * args.scale, cn, cnnz, free)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.shape) + (" (scaled x%g)" % args.scale if args.scale != 1.0 else ""),
-                           "nnz": nnz, "parallelism": "1 GPU" if world == 1 else "1-D node partition x%d" % world,
+                           "nnz": nnz, "parallelism": "1 GPU" if world == 1 else "1-D node partition x%d (equal node ranges)" % world,
                            "launch": "CUDA graph replay of one captured step" if graphed else "eager launches",
-                           "l2": "working set (weight_I 2.67 GB, X 1.0 GB, edge lists) exceeds the 126 MB L2; no flush needed"},
+                           "feature_term": "per-basis projection on tcgen05 + table mixing" if fused else "per-edge messages",
+                           "l2": "working set (identity table, features, edge lists: GBs) exceeds the 126 MB L2; no flush needed"
+                                 if nnz > 5e6 else "working set fits the 126 MB L2 (small graph): numbers are L2-resident"},
                 "e2e": {"value": nnz / (ms_e2e_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e_step, "steps": e_steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels}
+        if parity is not None:
+            line["parity_vs_n1"] = parity["max_rel_err"]
+            line["parity_detail"] = parity
+        if collectives is not None:
+            line["collectives"] = collectives
+        if lp_extra is not None:
+            line["lp"] = lp_extra
         print(json.dumps(line), flush=True)
     if world > 1:
         # A captured CUDA graph holds NCCL kernels of this communicator; tearing the process group down with the graph

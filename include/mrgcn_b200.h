@@ -205,7 +205,15 @@ typedef struct mrgcn_layer_bwd_args {
   float *gact, *cbuf, *part, *g_wmix, *colsum_ws;
   float *wt_ws;   /* [R*in*out]  (g_X wanted) transposed weights */
   float *msgx_ws; /* [E_F*mrgcn_msg_stride(in)] (g_X wanted) per-edge input-gradient messages */
+  /* phases: 0 = everything in one call; otherwise a mask of MRGCN_BWD_* - the node-partitioned model first asks for
+   * ACT | GX (the input gradient feeds a reduce-scatter), records an event, and then for the weight gradients, so that
+   * the collective runs under them.  gact must be the same buffer in both calls. */
+  int32_t phases, _pad;
 } mrgcn_layer_bwd_args;
+#define MRGCN_BWD_ACT   1 /* gact = gout * relu' * mask, bias gradient */
+#define MRGCN_BWD_IDENT 2 /* g_weight_I, g_comp_I */
+#define MRGCN_BWD_FEATW 4 /* g_weight_F, g_comp_F */
+#define MRGCN_BWD_GX    8 /* g_X */
 int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_t stream);
 
 /* DistMult scorer.  Replaces score_distmult_bc (mrgcn/tasks/link_prediction.py:645-665), generic path:

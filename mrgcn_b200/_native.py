@@ -71,7 +71,11 @@ class LayerBwdArgs(C.Structure):
         ("g_comp_F", C.c_void_p), ("g_bias", C.c_void_p), ("g_X", C.c_void_p),
         ("gact", C.c_void_p), ("cbuf", C.c_void_p), ("part", C.c_void_p), ("g_wmix", C.c_void_p),
         ("colsum_ws", C.c_void_p), ("wt_ws", C.c_void_p), ("msgx_ws", C.c_void_p),
+        ("phases", C.c_int32), ("_pad", C.c_int32),
     ]
+
+
+BWD_ACT, BWD_IDENT, BWD_FEATW, BWD_GX = 1, 2, 4, 8
 
 
 # name -> (restype, argtypes); every symbol include/mrgcn_b200.h declares

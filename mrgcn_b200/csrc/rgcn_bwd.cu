@@ -40,13 +40,14 @@ static int set_smem(K kernel, size_t bytes) {
 __global__ void __launch_bounds__(kThreads)
 k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const float *__restrict__ mask,
           float *__restrict__ gact, float *__restrict__ colsum, int ND, int od, int relu) {
-  extern __shared__ float red[];  // [kThreads]
+  extern __shared__ double red[];  // [kThreads]; the (small) bias sums are accumulated in double: the result is then as
+                                   // close to the exact sum as the fp32 inputs allow, whatever the order
   const int r0 = blockIdx.x * kColRows, r1 = min(ND, r0 + kColRows);
   const int oc = min(od, kThreads), nslots = kThreads / oc;
   const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
   for (int o0 = 0; o0 < od; o0 += oc) {
     const int o = o0 + ol;
-    float acc = 0.f;
+    double acc = 0.0;
     if (slot < nslots && o < od) {
       for (int i = r0 + slot; i < r1; i += nslots) {
         size_t x = (size_t)i * od + o;
@@ -63,7 +64,7 @@ k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const 
       if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
       __syncthreads();
     }
-    if (colsum && slot == 0 && o < od) colsum[(size_t)blockIdx.x * od + o] = red[ol];
+    if (colsum && slot == 0 && o < od) colsum[(size_t)blockIdx.x * od + o] = (float)red[ol];
     __syncthreads();
   }
 }
@@ -73,12 +74,12 @@ k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const 
 __global__ void __launch_bounds__(256)
 k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_idx,
              int nall, int width, float *__restrict__ outp) {
-  __shared__ float red[8][32];
+  __shared__ double red[8][32];   // partial sums of thousands of fp32 terms: accumulated in double (tiny kernels)
   const int s = blockIdx.y;
   const int xl = threadIdx.x & 31, slot = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + xl;
   const int lo = seg_ptr ? seg_ptr[s] : 0, hi = seg_ptr ? seg_ptr[s + 1] : nall;
-  float a0 = 0.f, a1 = 0.f;
+  double a0 = 0.0, a1 = 0.0;
   if (x < width) {
     int c = lo + slot;
     for (; c + 8 < hi; c += 16) {
@@ -90,8 +91,8 @@ k_seq_reduce(const float *__restrict__ part, const int32_t *__restrict__ seg_ptr
   red[slot][xl] = a0 + a1;
   __syncthreads();
   if (slot == 0 && x < width) {
-    float t = ((red[0][xl] + red[1][xl]) + (red[2][xl] + red[3][xl])) + ((red[4][xl] + red[5][xl]) + (red[6][xl] + red[7][xl]));
-    outp[(size_t)s * width + x] = t;
+    double t = ((red[0][xl] + red[1][xl]) + (red[2][xl] + red[3][xl])) + ((red[4][xl] + red[5][xl]) + (red[6][xl] + red[7][xl]));
+    outp[(size_t)s * width + x] = (float)t;
   }
 }
 
@@ -428,14 +429,14 @@ __global__ void k_ident_bwd_w_combine(HubSegs h, float *__restrict__ gW, int64_t
 __global__ void __launch_bounds__(kThreads)
 k_comp_chunk_reduce(const float *__restrict__ cbuf, const int32_t *__restrict__ chunk_ptr,
                     const int32_t *__restrict__ e3_to_e2, float *__restrict__ part, int B) {
-  __shared__ float red[kThreads];
+  __shared__ double red[kThreads];
   const int c = blockIdx.x;
   const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
   const int bc = min(B, kThreads), nslots = kThreads / bc;
   const int slot = threadIdx.x / bc, bl = threadIdx.x - slot * bc;
   for (int b0 = 0; b0 < B; b0 += bc) {
     const int b = b0 + bl;
-    float acc = 0.f;
+    double acc = 0.0;
     if (slot < nslots && b < B)
       for (int e = e_lo + slot; e < e_hi; e += nslots) acc += cbuf[(size_t)e3_to_e2[e] * B + b];
     if (slot < nslots) red[slot * bc + bl] = acc;
@@ -444,7 +445,7 @@ k_comp_chunk_reduce(const float *__restrict__ cbuf, const int32_t *__restrict__ 
       if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * bc + bl] += red[(slot + s) * bc + bl];
       __syncthreads();
     }
-    if (slot == 0 && b < B) part[(size_t)c * B + b] = red[bl];
+    if (slot == 0 && b < B) part[(size_t)c * B + b] = (float)red[bl];
     __syncthreads();
   }
 }
@@ -650,17 +651,18 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   const mrgcn_graph *gI = f.gI, *gF = f.gF;
   const int ND = hasI ? gI->ND : gF->ND;
   MRGCN_REQUIRE(!f.relu || f.out, MRGCN_E_BADARG, "layer_bwd: relu needs the forward output");
+  const int ph = a->phases ? a->phases : (MRGCN_BWD_ACT | MRGCN_BWD_IDENT | MRGCN_BWD_FEATW | MRGCN_BWD_GX);
 
   // 1. gact and bias gradient
   const int nblk = (int)cdiv(ND > 0 ? ND : 1, kColRows);
   MRGCN_REQUIRE(!a->g_bias || a->colsum_ws, MRGCN_E_BADARG, "layer_bwd: colsum_ws missing");
-  if (ND > 0) {
+  if (ND > 0 && (ph & MRGCN_BWD_ACT)) {
     MRGCN_PROF("act_bwd");
-  k_act_bwd<<<nblk, kThreads, kThreads * sizeof(float), st>>>(a->gout, f.out, f.row_mask, a->gact,
+  k_act_bwd<<<nblk, kThreads, kThreads * sizeof(double), st>>>(a->gout, f.out, f.row_mask, a->gact,
                                                                  a->g_bias ? a->colsum_ws : nullptr, ND, out, f.relu);
     MRGCN_LAUNCH_CHECK();
   }
-  if (a->g_bias) {
+  if (a->g_bias && (ph & MRGCN_BWD_ACT)) {
     if (ND > 0) {
       MRGCN_PROF("bias_reduce");
   k_seq_reduce<<<dim3((unsigned)cdiv(out, 32), 1), 256, 0, st>>>(a->colsum_ws, nullptr, nullptr, nblk, out, a->g_bias);
@@ -671,7 +673,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   }
 
   // 2. identity term
-  if (hasI && a->g_weight_I) {
+  if (hasI && a->g_weight_I && (ph & MRGCN_BWD_IDENT)) {
     const int64_t NS = gI->NS;
     if (B == 0) {
       MRGCN_CUDA(cudaMemsetAsync(a->g_weight_I, 0, sizeof(float) * (size_t)gI->R * NS * out, st));
@@ -836,7 +838,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   if (hasF) {
     const int IO = in * out;
     const float *W = B > 0 ? f.wmix : f.weight_F;
-    if (a->g_weight_F || a->g_comp_F) {
+    if ((a->g_weight_F || a->g_comp_F) && (ph & MRGCN_BWD_FEATW)) {
       float *gW = B > 0 ? a->g_wmix : a->g_weight_F;
       MRGCN_REQUIRE(gW && a->part, MRGCN_E_BADARG, "layer_bwd: g_wmix/part missing");
       static int rw_mode = -1;   // MRGCN_FEAT_RW=0 selects the thread-per-row kernel everywhere
@@ -895,7 +897,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         }
       }
     }
-    if (a->g_X) {
+    if (a->g_X && (ph & MRGCN_BWD_GX)) {
       MRGCN_REQUIRE(a->wt_ws && a->msgx_ws, MRGCN_E_BADARG, "layer_bwd: wt_ws/msgx_ws missing");
       const int64_t NS = gF->NS;
       if (NS > 0) {

@@ -44,6 +44,15 @@ def _x_layout(X):
     return Xc, int(Xc.shape[1])
 
 
+def fused_projection_pitch(in_dim, B, out_dim):
+    """Row pitch (floats) the projection kernel wants for X when an input layer with identity and feature term and B
+    bases runs its feature term through csrc/feat_proj.cu + the table-term kernels; 0 when that path does not apply."""
+    if not B or B <= 0 or os.environ.get("MRGCN_PROJ", "1") == "0" or not _tab_mode(B, out_dim):
+        return 0
+    pitch = int(nv.lib().mrgcn_feat_proj_supported(in_dim, B, out_dim))
+    return pitch if pitch and (int(nv.lib().mrgcn_tab_mode(B, B, out_dim)) & 1) else 0
+
+
 def _hub_ws(gI, gF, in_dim, out_dim, B, dev):
     """Workspace for the partial sums of hub segments (include/mrgcn_b200.h: hub_ws)."""
     segs = max([max(g.n_row_segs, g.n_col_segs) for g in (gI, gF) if g is not None] + [0])
@@ -87,9 +96,9 @@ class _LayerFn(torch.autograd.Function):
         # ... with identity AND feature term: project the features per basis on the tensor cores (csrc/feat_proj.cu) and
         # mix both tables in one pass; no per-edge feature messages then
         proj = vt_ws = xpad_ws = None
-        if plan is not None and hasF and gI is gF and os.environ.get("MRGCN_PROJ", "1") != "0":
-            pitch = int(nv.lib().mrgcn_feat_proj_supported(in_dim, B, out_dim))
-            if pitch and (int(nv.lib().mrgcn_tab_mode(B, B, out_dim)) & 1):
+        if plan is not None and hasF and gI is gF:
+            pitch = fused_projection_pitch(in_dim, B, out_dim)
+            if pitch:
                 proj = _empty(gI.NS * B * out_dim, dev)
                 vt_ws = _empty(2 * B * out_dim * pitch, dev)
                 if x_stride != pitch:
@@ -173,6 +182,15 @@ class _LayerFn(torch.autograd.Function):
         hub_ws = _hub_ws(gI if hasI else None, gF if hasF else None, in_dim, out_dim, B, dev)
         f.hub_ws = nv.ptr(hub_ws)
         with torch.cuda.device(dev):
+            if g_X is not None and not hasI and torch.distributed.is_available() and torch.distributed.is_initialized():
+                # hidden layer of a node-partitioned run: the input gradient feeds a reduce-scatter (partition.GatherRows);
+                # compute it first and mark the point where it is ready, so that the collective can run on a side stream
+                # under the weight-gradient kernels launched next
+                b.phases = nv.BWD_ACT | nv.BWD_GX
+                nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
+                g_X._mrgcn_ready = torch.cuda.Event()
+                g_X._mrgcn_ready.record()
+                b.phases = nv.BWD_IDENT | nv.BWD_FEATW
             nv.check(nv.lib().mrgcn_rgcn_layer_bwd(C.byref(b), nv.stream_ptr()), "rgcn_layer_bwd")
         g_add = gact[:g0.ND * out_dim].view(g0.ND, out_dim) if (ctx.has_addend and need[11]) else None
         return (g_X, g_wI, g_cI, g_wF, g_cF, g_b, None, None, None, None, None, g_add)

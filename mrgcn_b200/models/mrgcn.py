@@ -116,7 +116,19 @@ class MRGCN(nn.Module):
         else:
             self.gate_weights.requires_grad = False
 
-        self.rgcn = RGCN(modules, num_relations, num_nodes, num_bases, p_dropout, featureless, bias, link_prediction)
+        # One process per GPU under torchrun: the relational part is node-partitioned (mrgcn_b200/partition.py).  The ranges
+        # are fixed here, by node count, because the task loops build their optimizer from the parameters right after
+        # construction (node_classification.py:26-45) - before the model has seen the graph.
+        import torch.distributed as dist
+        self.partitioned = bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        if self.partitioned:
+            from ..partition import PartitionedRGCN, equal_bounds
+            assert p_dropout == 0.0, "node dropout is not supported by the partitioned model"
+            self.rgcn = PartitionedRGCN(modules, num_relations, num_nodes, num_bases, featureless, bias, link_prediction,
+                                        equal_bounds(num_nodes, dist.get_world_size()), dist.get_rank())
+            self.rgcn.enable_grad_hooks()
+        else:
+            self.rgcn = RGCN(modules, num_relations, num_nodes, num_bases, p_dropout, featureless, bias, link_prediction)
 
         # The kernels are CUDA-only: the relational part always lives on the GPU.  `gcn_gpu_acceleration`
         # (node_classification.py:390-392; never forwarded by link_prediction.py:466-471) is accepted and
@@ -143,13 +155,34 @@ class MRGCN(nn.Module):
             XF = self._compute_modality_embeddings(F, batch_idx)
             X = torch.as_tensor(X).to(self.X_device)
             X_dev = torch.cat([X.to(XF.dtype), XF], dim=1).to(rgcn_device)           # mrgcn.py:199-204
-        elif not self.rgcn.layers["layer_0"].featureless:
+        elif not self.rgcn.layers["layer_0"].featureless and not self.partitioned:
             # extension: pre-computed node features handed over as batch.X[0] (BASELINE.json config 3);
             # the reference has no encoder-free feature path (mrgcn.py:192-207 leaves X_dev = None)
             X_dev = self._upload_features(torch.as_tensor(X), rgcn_device)
+        if self.partitioned:
+            return self._forward_partitioned(X if X_dev is None else X_dev, batch.A)
         if X_dev is not None:
             X_dev = X_dev.float()
         return self.rgcn(X_dev, batch.A)
+
+    def _forward_partitioned(self, X, A):
+        """Node-partitioned forward: every rank hands over the SAME batch (as the reference's single process would); the rank
+        builds its share of the graph on first sight of A, uploads only the feature rows it needs and returns the logits of
+        ALL nodes (true node order), so that the caller's indexing with global node ids keeps working."""
+        rg, dev = self.rgcn, self.devices["relational"]
+        lay = rg.lay
+        if rg.gF is None or getattr(self, "_part_A", None) is not A:
+            idx = A._indices().to(dev)
+            rg.set_graph(idx[0], idx[1], A._values().to(dev).float())
+            self._part_A = A
+        if rg.layers["layer_0"].featureless:
+            return rg.forward_all(None)
+        X = torch.as_tensor(X)
+        if rg.layer0_is_source_partitioned():
+            X_in = X[lay.lo:lay.hi].to(dev, non_blocking=True).float()          # own rows only
+        else:
+            X_in = lay.to_padded(X.to(dev, non_blocking=True).float())
+        return rg.forward_all(X_in)
 
     def _upload_features(self, X, dev):
         """Host feature matrix -> device, every call (as mrgcn.py:203-204 does).  One contiguous DMA (a pitched 2-D copy of

@@ -9,7 +9,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for (N, P, T, dims, B, fl) in [(5000, 6, 40000, (24, 10, 11), 5, False), (4000, 5, 30000, (0, 16, 4), 0, True), (3000, 4, 20000, (0, 8), 3, True)]:
+for (N, P, T, dims, B, fl) in [(5000, 6, 40000, (24, 10, 11), 5, False), (6000, 6, 50000, (151, 10, 11), 40, False), (4000, 5, 30000, (0, 16, 4), 0, True), (3000, 4, 20000, (0, 8), 3, True)]:
     R = 2 * P + 1
     tr = synth_triples(N, P, T, seed=3)
     full = RelGraph.from_triples(tr, N, P, device=dev)
@@ -27,7 +27,8 @@ for (N, P, T, dims, B, fl) in [(5000, 6, 40000, (24, 10, 11), 5, False), (4000, 
     m = PartitionedRGCN(modules, R, N, B if B else -1, fl, True, False, bounds, rank)
     m.load_full_state(state); m.to(dev); m.set_graph(row, col, val)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    out = m(X.to(dev) if X is not None else None)
+    X_in = None if X is None else (X[lo:hi].to(dev) if m.layer0_is_source_partitioned() else m.lay.to_padded(X.to(dev)))
+    out = m(X_in)
     (out * G[lo:hi].to(dev)).sum().backward(); m.sync_grads()
     def chk(a, b, what):
         global ok
@@ -41,6 +42,14 @@ for (N, P, T, dims, B, fl) in [(5000, 6, 40000, (24, 10, 11), 5, False), (4000, 
             S = want.shape[0] // N
             want = want.view(S, N, -1)[:, lo:hi, :].reshape(S * (hi - lo), -1)
         chk(p.grad, want, n)
+    # a checkpoint written by the partitioned run is in the reference layout: it loads into the single-GPU model
+    sd = m.state_dict()
+    for k_, v_ in state.items():
+        if not torch.equal(sd[k_].cpu(), v_.cpu()):
+            ok = False; print("rank", rank, "state_dict MISMATCH", k_)
+    # what the drop-in returns: the logits of ALL nodes, true node order, on every rank
+    with torch.no_grad():
+        chk(m.forward_all(X_in), out_ref.detach(), "forward_all")
     if rank == 0: print("case", N, dims, B, "done; ok so far:", ok, "bounds", bounds.tolist())
 t = torch.tensor([1.0 if ok else 0.0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0: print("MULTIGPU PARITY", "PASS" if t.item() == 1.0 else "FAIL")

@@ -34,17 +34,17 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     from mrgcn_b200 import _native
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
-                    'int main(void){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(mrgcn_graph), sizeof(mrgcn_layer_args),'
+                    'int main(void){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(mrgcn_graph), sizeof(mrgcn_layer_args),'
                     ' sizeof(mrgcn_layer_bwd_args), offsetof(mrgcn_graph, long_rows), offsetof(mrgcn_graph, n_chunks),'
                     ' offsetof(mrgcn_layer_args, addend), offsetof(mrgcn_layer_bwd_args, gact), sizeof(mrgcn_tab_plan),'
-                    ' offsetof(mrgcn_tab_plan, n_blks), offsetof(mrgcn_layer_args, x_stride));return 0;}\n' % HEADER)
+                    ' offsetof(mrgcn_tab_plan, n_blks), offsetof(mrgcn_layer_args, x_stride), offsetof(mrgcn_layer_bwd_args, phases));return 0;}\n' % HEADER)
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-o", str(exe), str(prog)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(_native.Graph), ctypes.sizeof(_native.LayerArgs), ctypes.sizeof(_native.LayerBwdArgs),
             _native.Graph.long_rows.offset, _native.Graph.n_chunks.offset, _native.LayerArgs.addend.offset,
             _native.LayerBwdArgs.gact.offset, ctypes.sizeof(_native.TabPlan), _native.TabPlan.n_blks.offset,
-            _native.LayerArgs.x_stride.offset]
+            _native.LayerArgs.x_stride.offset, _native.LayerBwdArgs.phases.offset]
     assert got == want
 
 

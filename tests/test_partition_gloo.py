@@ -26,7 +26,7 @@ def test_balanced_bounds():
 
 
 def test_split_coo_partitions_every_entry_once():
-    from mrgcn_b200.partition import balanced_bounds, node_weights, split_coo
+    from mrgcn_b200.partition import _Layout, balanced_bounds, node_weights, split_coo
     from mrgcn_b200.synth import synth_triples
     N, P = 300, 4
     R = 2 * P + 1
@@ -34,14 +34,21 @@ def test_split_coo_partitions_every_entry_once():
     row, col, val = (torch.from_numpy(np.asarray(a)) for a in (A.row.astype(np.int64), A.col.astype(np.int64), A.data))
     bounds = balanced_bounds(node_weights(row, col, N), 3)
     nf = ni = 0
+    seen = torch.zeros(N, dtype=torch.bool)
     for p in range(3):
-        lo, hi = int(bounds[p]), int(bounds[p + 1])
-        (fr, fc, fv), (ir, ic, iv) = split_coo(row, col, val, N, R, lo, hi)
+        lay = _Layout(bounds, p)
+        assert lay.maxrows % 4 == 0 and lay.NP == 3 * lay.maxrows >= N
+        ids = torch.arange(lay.lo, lay.hi)
+        assert torch.equal(lay.pad_ids(ids), p * lay.maxrows + torch.arange(lay.n_own))      # own rows: one contiguous block
+        seen[ids] = True
+        (fr, fc, fv), (ir, ic, iv) = split_coo(row, col, val, N, R, lay)
         nf += len(fr)
         ni += len(ir)
-        assert fr.min() >= 0 and fr.max() < hi - lo and fc.max() < R * N
-        assert ir.max() < N and ic.max() < R * (hi - lo)
-    assert nf == len(row) and ni == len(row)
+        assert fr.min() >= 0 and fr.max() < lay.n_own and fc.max() < R * lay.NP     # rows local, sources in the padded layout
+        assert ir.max() < lay.NP and ic.max() < R * lay.n_own                        # rows in the padded layout, sources local
+        x = torch.arange(N * 2, dtype=torch.float32).view(N, 2)
+        assert torch.equal(lay.to_padded(x)[lay.own], x[lay.lo:lay.hi])
+    assert nf == len(row) and ni == len(row) and bool(seen.all())
 
 
 def _oracle_layer(X, weight_I, comp_I, weight_F, comp_F, bias, row_mask, gI, gF, B, relu, addend=None):
@@ -72,7 +79,7 @@ def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from mrgcn_b200.partition import PartitionedRGCN, balanced_bounds, node_weights
+        from mrgcn_b200.partition import PartitionedRGCN, _Layout, balanced_bounds, node_weights
         from mrgcn_b200.synth import synth_triples
         N, P = 200, 3
         R = 2 * P + 1
@@ -81,8 +88,10 @@ def _worker(rank, world, port, tmp):
         row, col, val = (torch.from_numpy(np.asarray(a)) for a in (coo.row.astype(np.int64), coo.col.astype(np.int64), coo.data))
         bounds = balanced_bounds(node_weights(row, col, N), world)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        # (dims, bases, featureless): 2-layer featureful NC, 2-layer featureless NC without bases, 1-layer LP-style encoder
-        for dims, B, fl in (((5, 6, 3), 2, False), ((0, 6, 3), -1, True), ((0, 8), 2, True)):
+        # (dims, bases, featureless): 2-layer featureful NC (feature term of layer 0 destination-partitioned), the same with a
+        # shape the projection path covers (layer 0 entirely source-partitioned, X sharded), 2-layer featureless NC without
+        # bases, 1-layer LP-style encoder
+        for dims, B, fl in (((5, 6, 3), 2, False), ((32, 4, 3), 4, False), ((0, 6, 3), -1, True), ((0, 8), 2, True)):
             torch.manual_seed(0)
             modules = [(dims[k], dims[k + 1], "mrgcn", nn.ReLU() if (k + 2 < len(dims) or len(dims) == 2) else None)
                        for k in range(len(dims) - 1)]
@@ -98,8 +107,23 @@ def _worker(rank, world, port, tmp):
             (ref * G).sum().backward()
             model = PartitionedRGCN(modules, R, N, B, fl, True, False, bounds, rank, layer_fn=_oracle_layer, graph_fn=_coo_graph)
             model.set_graph(row, col, val)
-            model.load_full_state({"layers.layer_%d.%s" % (k, n): v.detach() for k, l in enumerate(layers) for n, v in l.items()})
-            out = model(X)
+            # replicated parameters are broadcast from rank 0 when the graph is set: equal on every rank without any loading
+            flat = torch.cat([p.detach().reshape(-1) for p in model.replicated_parameters()])
+            both = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            assert all(torch.equal(both[0], b) for b in both)
+            full_state = {"layers.layer_%d.%s" % (k, n): v.detach() for k, l in enumerate(layers) for n, v in l.items()}
+            model.load_full_state(full_state)
+            # state_dict() is in the reference layout again (weight_I gathered), so checkpoints are interchangeable
+            sd = model.state_dict()
+            for k_, v_ in full_state.items():
+                assert torch.equal(sd[k_], v_), k_
+            assert model.layer0_is_source_partitioned() == (fl or dims[0] == 32)
+            X_in = None if fl else (X[lo:hi] if model.layer0_is_source_partitioned() else model.lay.to_padded(X))
+            out = model(X_in)
+            if len(dims) == 3:      # what a caller of the drop-in sees: all rows, true node order, on every rank
+                with torch.no_grad():
+                    assert torch.allclose(model.forward_all(X_in), ref.detach(), rtol=1e-5, atol=1e-6)
             assert out.shape == (hi - lo, dims[-1])
             assert torch.allclose(out, ref[lo:hi].detach(), rtol=1e-5, atol=1e-6), (dims, float((out - ref[lo:hi]).abs().max()))
             (out * G[lo:hi]).sum().backward()
