@@ -103,7 +103,9 @@ typedef struct mrgcn_graph {
 typedef struct mrgcn_tab_plan {
   int32_t n_tasks, n_wsrc, n_tiles, n_pieces, tile_slots, lt, _pad0, _pad1;
   int32_t *task_src, *task_lo;   /* [n_tasks] source and first E2 edge of task t */
+  int32_t *tasks4;               /* [n_tasks][4] {source, first edge, number of edges, 0}: one 16-byte load per task */
   int32_t *wsrc;                 /* [n_wsrc] */
+  int32_t *wtasks4;              /* [n_wsrc][4] {source, first edge, number of edges, 0} of the non-hub sources */
   int32_t *tile_task_ptr;        /* [n_tiles+1] */
   int32_t *tile_e0;              /* [n_tiles] first E2 edge of the tile */
   int32_t *tperm;                /* [E] */

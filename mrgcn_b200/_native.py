@@ -42,7 +42,8 @@ class TabPlan(C.Structure):
     _fields_ = [
         ("n_tasks", C.c_int32), ("n_wsrc", C.c_int32), ("n_tiles", C.c_int32), ("n_pieces", C.c_int32),
         ("tile_slots", C.c_int32), ("lt", C.c_int32), ("_pad0", C.c_int32), ("_pad1", C.c_int32),
-        ("task_src", C.c_void_p), ("task_lo", C.c_void_p), ("wsrc", C.c_void_p), ("tile_task_ptr", C.c_void_p),
+        ("task_src", C.c_void_p), ("task_lo", C.c_void_p), ("tasks4", C.c_void_p), ("wsrc", C.c_void_p),
+        ("wtasks4", C.c_void_p), ("tile_task_ptr", C.c_void_p),
         ("tile_e0", C.c_void_p), ("tperm", C.c_void_p), ("piece_ptr", C.c_void_p), ("tile_piece_ptr", C.c_void_p),
         ("rel_piece_ptr", C.c_void_p), ("rel_piece_idx", C.c_void_p), ("blk_ptr", C.c_void_p), ("rel_blk_ptr", C.c_void_p),
         ("n_blks", C.c_int32), ("_pad2", C.c_int32),

@@ -22,6 +22,7 @@
 // traffic for the table at all (the round-1 kernels were bound by the shared-memory pipe: one 8-byte read per 2 FMAs).
 // All reductions have a fixed order: bit-reproducible, no float atomics.
 #include "common.cuh"
+#include "pipeline.cuh"
 #include "rgcn_internal.cuh"
 
 namespace mrgcn {
@@ -64,6 +65,15 @@ __device__ __forceinline__ void fill_comp(float *comp_s, const float *__restrict
   }
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): metadata of the NEXT item lands while the current one is computed
+__device__ __forceinline__ void cp4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// {source, first E2 edge, number of edges, -} of task / source t, or an empty task
+__device__ __forceinline__ int4 ld_task(const int4 *__restrict__ tasks, int t, int n, bool lane_on) {
+  return (lane_on && t < n) ? __ldg(tasks + t) : make_int4(0, 0, 0, 0);
+}
+
 template <bool EVEN>
 __device__ __forceinline__ float2 ld2(const float *p, bool second) {
   if constexpr (EVEN) return *reinterpret_cast<const float2 *>(p);
@@ -95,38 +105,51 @@ __device__ __forceinline__ void load_rows(float2 (&T)[BPT][NOP], const TabTables
 template <int BPT, int NOP, bool EVEN>
 __global__ void __launch_bounds__(kTabThreads, 2)
 k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__restrict__ compF, int R,
-              const int32_t *__restrict__ colptr, const int32_t *__restrict__ task_src, const int32_t *__restrict__ task_lo,
-              int n_tasks, const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, float *__restrict__ msg,
-              int ms, int GS, int HS, int CSP) {
+              const int4 *__restrict__ tasks, int n_tasks, const int32_t *__restrict__ e2_rel,
+              const float *__restrict__ e2_val, float *__restrict__ msg, int ms, int GS, int HS, int CSP) {
   extern __shared__ __align__(16) float smem[];
   float *comp_s = smem;                                             // [R][CSP]
-  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)R * CSP);    // [warps][TPW*LT] (rel, val)
+  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)R * CSP);    // [warps][2][TPW*LT] (rel, val), double buffered
   fill_comp(comp_s, compI, compF, R, tb.BI, tb.BF, CSP);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g(GS, HS, lane);
   const int out = tb.out;
-  int2 *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task
+  int2 *tmeta = meta + ((size_t)warp * 2 * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task, buffer 0
+  const int bufstride = g.TPW * LT;
   const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_tasks + g.TPW - 1) / g.TPW;
   const bool writer = g.hs == 0 && g.lane_on;
-  for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
-    const int t = wi * g.TPW + g.tslot;
-    const bool on = g.lane_on && t < n_tasks;
-    int j = 0, lo = 0, len = 0;
-    if (on) { j = task_src[t]; lo = task_lo[t]; len = min(LT, colptr[j + 1] - lo); }
-    __syncwarp();                              // previous item done with the metadata
-    for (int s = g.within; s < len; s += g.LPT)
-      tmeta[s] = make_int2(ldg_stream(e2_rel + lo + s), __float_as_int(ldg_stream(e2_val + lo + s)));
+  const int stride = gridDim.x * kTabWarps;
+  auto stage = [&](int buf, const int4 &ti) {      // this lane's share of its task's metadata, asynchronously
+    int2 *dst = tmeta + buf * bufstride;
+    for (int s = g.within; s < ti.z; s += g.LPT) {
+      cp4(&dst[s].x, e2_rel + ti.y + s);
+      cp4(&dst[s].y, e2_val + ti.y + s);
+    }
+    cp_async_commit();
+  };
+  int wi = blockIdx.x * kTabWarps + warp;
+  int4 cur = ld_task(tasks, wi * g.TPW + g.tslot, n_tasks, g.lane_on && wi < n_items);
+  int4 nxt = ld_task(tasks, (wi + stride) * g.TPW + g.tslot, n_tasks, g.lane_on && wi + stride < n_items);
+  stage(0, cur);
+  for (int it = 0; wi < n_items; wi += stride, ++it) {
+    // task descriptors two items ahead, metadata one item ahead, table rows of this item: all in flight together
+    const int4 nn = ld_task(tasks, (wi + 2 * stride) * g.TPW + g.tslot, n_tasks, g.lane_on && wi + 2 * stride < n_items);
+    stage((it + 1) & 1, nxt);
+    const bool on = cur.z > 0;
+    const int len = cur.z;
     float2 T[BPT][NOP];
-    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, j, g.op0, on);
+    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, cur.x, g.op0, on);
+    cp_async_wait<1>();
     __syncwarp();
+    const int2 *mbuf = tmeta + (it & 1) * bufstride;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    float *mrow = msg + (size_t)lo * ms + 2 * g.op0;
+    float *mrow = msg + (size_t)cur.y * ms + 2 * g.op0;
     for (int s = 0; s < maxlen; ++s, mrow += ms) {
       const bool live = s < len;
       int2 m = make_int2(0, 0);
-      if (live) m = tmeta[s];
+      if (live) m = mbuf[s];
       const float *cr = cbase + m.x * CSP;
       float2 acc[NOP], acc1[NOP];   // two chains per output pair (even / odd groups of four bases), added at the end
 #pragma unroll
@@ -169,7 +192,11 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
           if (NOP == 1 || 2 * (g.op0 + 32 * q) < out) *reinterpret_cast<float2 *>(mrow + 64 * q) = make_float2(v * acc[q].x, v * acc[q].y);
       }
     }
+    __syncwarp();      // the buffer just read is re-staged by the next iteration
+    cur = nxt;
+    nxt = nn;
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -177,41 +204,56 @@ struct __align__(16) EdgeMeta { int d, r; float v; int pad; };
 
 template <int BPT, int NOP, bool EVEN>
 __global__ void __launch_bounds__(kTabThreads, (BPT * NOP > 24) ? 1 : 2)
-k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out, const int32_t *__restrict__ colptr,
-            const int32_t *__restrict__ wsrc, int n_src, const int32_t *__restrict__ e2_dst,
-            const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val, const float *__restrict__ gact,
-            float *__restrict__ gW, int GS, int HS, int CSP) {
+k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out, const int4 *__restrict__ wtasks, int n_src,
+            const int32_t *__restrict__ e2_dst, const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
+            const float *__restrict__ gact, float *__restrict__ gW, int GS, int HS, int CSP) {
   extern __shared__ __align__(16) float smem[];
   float *comp_s = smem;                                                     // [R][CSP]
-  EdgeMeta *meta = reinterpret_cast<EdgeMeta *>(smem + (size_t)R * CSP);    // [warps][TPW*32]
+  EdgeMeta *meta = reinterpret_cast<EdgeMeta *>(smem + (size_t)R * CSP);    // [warps][2][TPW*32], double buffered
   fill_comp(comp_s, compI, nullptr, R, BI, 0, CSP);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g(GS, HS, lane);
-  EdgeMeta *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * 32;
+  EdgeMeta *tmeta = meta + ((size_t)warp * 2 * g.TPW + (g.lane_on ? g.tslot : 0)) * 32;
+  const int bufstride = g.TPW * 32;
   const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_src + g.TPW - 1) / g.TPW;
-  for (int wi = blockIdx.x * kTabWarps + warp; wi < n_items; wi += gridDim.x * kTabWarps) {
-    const int t = wi * g.TPW + g.tslot;
-    const bool on = g.lane_on && t < n_src;
-    int j = 0, e_lo = 0, len = 0;
-    if (on) { j = wsrc[t]; e_lo = colptr[j]; len = colptr[j + 1] - e_lo; }
+  const int stride = gridDim.x * kTabWarps;
+  auto stage = [&](int buf, const int4 &ti, int c0) {      // edges [c0, c0 + 32) of this lane's source
+    EdgeMeta *dst = tmeta + buf * bufstride;
+    const int n = min(32, ti.z - c0);
+    for (int s = g.within; s < n; s += g.LPT) {
+      const int e = ti.y + c0 + s;
+      cp4(&dst[s].d, e2_dst + e);
+      cp4(&dst[s].r, e2_rel + e);
+      cp4(&dst[s].v, e2_val + e);
+    }
+    cp_async_commit();
+  };
+  int wi = blockIdx.x * kTabWarps + warp;
+  int4 cur = ld_task(wtasks, wi * g.TPW + g.tslot, n_src, g.lane_on && wi < n_items);
+  int4 nxt = ld_task(wtasks, (wi + stride) * g.TPW + g.tslot, n_src, g.lane_on && wi + stride < n_items);
+  stage(0, cur, 0);
+  int buf = 0;
+  for (; wi < n_items; wi += stride) {
+    const int4 nn = ld_task(wtasks, (wi + 2 * stride) * g.TPW + g.tslot, n_src, g.lane_on && wi + 2 * stride < n_items);
+    const bool on = g.lane_on && wi * g.TPW + g.tslot < n_src;
+    const int j = cur.x, len = cur.z;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
     float2 acc[BPT][NOP];
 #pragma unroll
     for (int b = 0; b < BPT; ++b)
 #pragma unroll
       for (int q = 0; q < NOP; ++q) acc[b][q] = make_float2(0.f, 0.f);
-    for (int c0 = 0; c0 < maxlen; c0 += 32) {
+    int c0 = 0;
+    do {
+      // the next 32 edges of these sources, or the first 32 of the next item's, are fetched under this chunk's arithmetic
+      if (c0 + 32 < maxlen) stage(buf ^ 1, cur, c0 + 32);
+      else stage(buf ^ 1, nxt, 0);
+      cp_async_wait<1>();
+      __syncwarp();
+      const EdgeMeta *mbuf = tmeta + buf * bufstride;
       const int mylen = min(32, max(0, len - c0));
-      __syncwarp();
-      for (int s = g.within; s < mylen; s += g.LPT) {
-        const int e = e_lo + c0 + s;
-        EdgeMeta m;
-        m.d = ldg_stream(e2_dst + e); m.r = ldg_stream(e2_rel + e); m.v = ldg_stream(e2_val + e); m.pad = 0;
-        tmeta[s] = m;
-      }
-      __syncwarp();
       const int nch = min(32, maxlen - c0);
       // groups of U edges; the gathers of group k+1 are in flight while group k is accumulated
       constexpr int U = (BPT * NOP >= 16) ? 2 : 4;
@@ -222,7 +264,7 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
         for (int u = 0; u < U; ++u) {
           const bool live = s0 + u < mylen;
           mm[u].d = 0; mm[u].r = 0; mm[u].v = 0.f;
-          if (live) mm[u] = tmeta[s0 + u];
+          if (live) mm[u] = mbuf[s0 + u];
           const float *gp = gact + (size_t)mm[u].d * out + 2 * g.op0;
 #pragma unroll
           for (int q = 0; q < NOP; ++q) {
@@ -258,7 +300,10 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
           }
         }
       }
-    }
+      __syncwarp();      // everybody is done with this buffer before it is staged again
+      buf ^= 1;
+      c0 += 32;
+    } while (c0 < maxlen);
     if (on) {
       const int b0 = g.hs * BPT;
       const size_t s1 = (size_t)NS * out;
@@ -282,7 +327,10 @@ k_tab_bwd_w(const float *__restrict__ compI, int R, int BI, int64_t NS, int out,
         }
       }
     }
+    cur = nxt;
+    nxt = nn;
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -471,7 +519,7 @@ int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const flo
   if (pl->n_tasks == 0) return 0;
   TabTables tb{TI, TP, BI, BF, out, (int64_t)g->NS};
   const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
-  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * LT * sizeof(int2);
+  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * 2 * TPW * LT * sizeof(int2);
   MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_msg_fwd: R*B too large for shared memory (%zu B)", smem);
   const int ms = msg_stride(out);
   const int64_t items = cdiv(pl->n_tasks, TPW);
@@ -480,9 +528,9 @@ int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const flo
   do {                                                                                                                \
     if (int rc = tab_set_smem(k_tab_msg_fwd<BPTV, NOPV, true>, smem)) return rc;                                            \
     const unsigned grid = tab_grid(k_tab_msg_fwd<BPTV, NOPV, true>, smem, cdiv(items, kTabWarps));                          \
-    k_tab_msg_fwd<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(tb, compI, compF, g->R, g->colptr, pl->task_src,      \
-                                                               pl->task_lo, pl->n_tasks, g->e2_rel, g->e2_val, msg,   \
-                                                               ms, geo.GS, geo.HS, geo.CSP);                          \
+    k_tab_msg_fwd<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(tb, compI, compF, g->R,                             \
+                                                               reinterpret_cast<const int4 *>(pl->tasks4), pl->n_tasks, \
+                                                               g->e2_rel, g->e2_val, msg, ms, geo.GS, geo.HS, geo.CSP); \
   } while (0)
   TAB_DISPATCH(CALL);
 #undef CALL
@@ -496,7 +544,7 @@ int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
   MRGCN_REQUIRE(tab_geometry(BI, out, geo, kBwdWBpt), MRGCN_E_NOTSUP, "tab_bwd_w: unsupported shape B=%d out=%d", BI, out);
   if (pl->n_wsrc == 0) return 0;
   const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
-  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * 32 * sizeof(EdgeMeta);
+  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * 2 * TPW * 32 * sizeof(EdgeMeta);
   MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_bwd_w: R*B too large for shared memory (%zu B)", smem);
   const int64_t items = cdiv(pl->n_wsrc, TPW);
   MRGCN_PROF("tab_bwd_w");
@@ -504,9 +552,10 @@ int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
   do {                                                                                                                \
     if (int rc = tab_set_smem(k_tab_bwd_w<BPTV, NOPV, true>, smem)) return rc;                                              \
     const unsigned grid = tab_grid(k_tab_bwd_w<BPTV, NOPV, true>, smem, cdiv(items, kTabWarps));                            \
-    k_tab_bwd_w<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(compI, g->R, BI, (int64_t)g->NS, out, g->colptr,        \
-                                                             pl->wsrc, pl->n_wsrc, g->e2_dst, g->e2_rel, g->e2_val,   \
-                                                             gact, gW, geo.GS, geo.HS, geo.CSP);                      \
+    k_tab_bwd_w<BPTV, NOPV, true><<<grid, kTabThreads, smem, st>>>(compI, g->R, BI, (int64_t)g->NS, out,                   \
+                                                             reinterpret_cast<const int4 *>(pl->wtasks4), pl->n_wsrc, \
+                                                             g->e2_dst, g->e2_rel, g->e2_val, gact, gW, geo.GS,       \
+                                                             geo.HS, geo.CSP);                                        \
   } while (0)
   TAB_DISPATCH(CALL);
 #undef CALL

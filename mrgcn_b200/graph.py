@@ -88,7 +88,12 @@ def build_tab_plan(colptr, e2_rel, E, NS, R, long_thresh, lt=TAB_LT, tile=TAB_TI
     # the gradient: their 8-byte stores fill whole sectors; ordering by degree was measured to turn them into
     # read-modify-write traffic, profiles/r02d_ncu_full_summary.txt)
     wsrc = torch.nonzero(deg <= long_thresh).flatten()
-    plan = dict(n_tasks=n_tasks, lt=lt, task_src=i32(task_src), task_lo=i32(task_lo), wsrc=i32(wsrc), n_wsrc=len(wsrc))
+    task_len = torch.minimum(torch.full_like(task_lo, lt), colptr[task_src + 1] - task_lo)
+    zero = torch.zeros_like(task_lo)
+    tasks4 = torch.stack([task_src, task_lo, task_len, zero], 1)                  # one 16-byte descriptor per task
+    wtasks4 = torch.stack([wsrc, colptr[wsrc], deg[wsrc], torch.zeros_like(wsrc)], 1)
+    plan = dict(n_tasks=n_tasks, lt=lt, task_src=i32(task_src), task_lo=i32(task_lo), wsrc=i32(wsrc), n_wsrc=len(wsrc),
+                tasks4=i32(tasks4), wtasks4=i32(wtasks4))
     if E == 0:
         z = torch.zeros(1, dtype=torch.int32, device=dev)
         zr = torch.zeros(R + 1, dtype=torch.int32, device=dev)
@@ -276,7 +281,7 @@ class RelGraph:
             c = nv.TabPlan()
             for k in ("n_tasks", "n_wsrc", "n_tiles", "n_pieces", "tile_slots", "lt", "n_blks"):
                 setattr(c, k, int(d[k]))
-            for k in ("task_src", "task_lo", "wsrc", "tile_task_ptr", "tile_e0", "tperm", "piece_ptr", "tile_piece_ptr",
+            for k in ("task_src", "task_lo", "tasks4", "wsrc", "wtasks4", "tile_task_ptr", "tile_e0", "tperm", "piece_ptr", "tile_piece_ptr",
                       "rel_piece_ptr", "rel_piece_idx", "blk_ptr", "rel_blk_ptr"):
                 if d[k].numel() == 0:
                     d[k] = torch.zeros(1, dtype=_I32, device=self.device)
