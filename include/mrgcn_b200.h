@@ -120,6 +120,8 @@ typedef struct mrgcn_tab_plan {
 /* which table-term kernels apply to (B_I identity bases, B_F projected feature bases, out): bit 0 forward messages,
  * bit 1 basis gradient, bit 2 comp gradient without the E x B scratch (cbuf then holds n_pieces x B records). */
 int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out);
+/* Which of them may be used at all (same bits; -1 = re-read MRGCN_TAB from the environment, default 1: messages only). */
+void mrgcn_set_tab_mask(int32_t mask);
 
 /* Re-emit the reference's stacked adjacency as E1/E2/E3.
  * Replaces: scipy CSR -> torch COO hand-off (mrgcn/data/utils.py:165-170, mrgcn/data/batch.py:144-149)

@@ -688,7 +688,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       const int OC = pick_oc(out);
       const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
       TabGeom tg;
-      const bool tab_w = f.plan && tab_geometry(B, out, tg, kBwdWBpt);
+      const bool tab_w = f.plan && (mrgcn_tab_mode(B, 0, out) & 2) && tab_geometry(B, out, tg, kBwdWBpt);
       {  // basis gradient
         if (tab_w) {
           if (int rc = launch_tab_bwd_w(gI, f.plan, f.comp_I, B, out, a->gact, a->g_weight_I, st)) return rc;
@@ -749,7 +749,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       if (a->g_comp_I) {
         MRGCN_REQUIRE(a->cbuf && a->part, MRGCN_E_BADARG, "layer_bwd: cbuf/part missing");
         int tBC = 0, tOP = 0;
-        const bool tab_c = f.plan && tab_c_geometry(B, out, tBC, tOP);
+        const bool tab_c = f.plan && (mrgcn_tab_mode(B, 0, out) & 4) && tab_c_geometry(B, out, tBC, tOP);
         if (tab_c) {
           // records of the (tile, relation) pieces, then the fixed-order sum per relation
           if (gI->E > 0)

@@ -655,7 +655,7 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
       MRGCN_REQUIRE(a->comp_I && a->msg_I, MRGCN_E_BADARG, "layer_fwd: comp_I/msg_I missing");
       TabGeom tg;
       // projected features: the feature term rides in the identity term's messages (one table pass, one message per edge)
-      fused_feat = hasF && a->proj && a->plan && gI == gF && feat_proj_supported(in, ldx, B, out) && tab_geometry(2 * B, out, tg);
+      fused_feat = hasF && a->proj && a->plan && gI == gF && (mrgcn_tab_mode(B, B, out) & 1) && feat_proj_supported(in, ldx, B, out) && tab_geometry(2 * B, out, tg);
       if (fused_feat) {
         MRGCN_REQUIRE(a->comp_F && a->vt_ws, MRGCN_E_BADARG, "layer_fwd: comp_F/vt_ws missing");
         if (int rc = launch_feat_proj(a->X, gI->NS, in, ldx, a->weight_F, B, out, a->vt_ws, a->xpad_ws, a->proj, st)) return rc;
@@ -663,7 +663,7 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
       if (gI->E > 0) {
         if (fused_feat) {
           if (int rc = launch_tab_msg_fwd(gI, a->plan, a->weight_I, a->comp_I, B, a->proj, a->comp_F, B, out, a->msg_I, st)) return rc;
-        } else if (a->plan && tab_geometry(B, out, tg)) {
+        } else if (a->plan && (mrgcn_tab_mode(B, 0, out) & 1) && tab_geometry(B, out, tg)) {
           if (int rc = launch_tab_msg_fwd(gI, a->plan, a->weight_I, a->comp_I, B, nullptr, nullptr, 0, out, a->msg_I, st)) return rc;
         } else {
           if (int rc = launch_ident_msg_fwd(gI, a->weight_I, a->comp_I, a->msg_I, B, out, st)) return rc;

@@ -21,6 +21,8 @@
 // bytes apart); here every table row is read from HBM exactly once per pass, straight into registers: no shared-memory
 // traffic for the table at all (the round-1 kernels were bound by the shared-memory pipe: one 8-byte read per 2 FMAs).
 // All reductions have a fixed order: bit-reproducible, no float atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pipeline.cuh"
 #include "rgcn_internal.cuh"
@@ -82,12 +84,27 @@ __device__ __forceinline__ float2 ld2(const float *p, bool second) {
 
 // The BPT table rows (x NOP output pairs) of one lane: bases [b0, b0 + BPT) of source j, the first n1 of them from the
 // basis-major identity table, the rest from the node-major projection; everything beyond Btot or `out` is zero.
+// The two common cases - all of the lane's bases in ONE table - walk a pointer (two instructions per load).
 template <int BPT, int NOP, bool EVEN>
 __device__ __forceinline__ void load_rows(float2 (&T)[BPT][NOP], const TabTables &tb, int b0, int64_t j, int op0, bool on) {
   const int out = tb.out, Btot = tb.BI + tb.BF;
   const int n1 = min(max(tb.BI - b0, 0), BPT);
   const int nvalid = on ? min(max(Btot - b0, 0), BPT) : 0;
   const size_t s1 = (size_t)tb.NS * out;
+  const bool o_ok = NOP > 1 || 2 * op0 < out;
+  if (nvalid == BPT && o_ok && (n1 == BPT || n1 == 0)) {
+    const float *p = n1 ? tb.TI + ((size_t)b0 * tb.NS + j) * out + 2 * op0 : tb.TP + ((size_t)j * tb.BF + (b0 - tb.BI)) * out + 2 * op0;
+    const size_t step = n1 ? s1 : (size_t)out;
+#pragma unroll
+    for (int b = 0; b < BPT; ++b, p += step) {
+#pragma unroll
+      for (int q = 0; q < NOP; ++q) {
+        const int o = 2 * (op0 + 32 * q);
+        T[b][q] = (NOP == 1 || o < out) ? ld2<EVEN>(p + 64 * q, o + 1 < out) : make_float2(0.f, 0.f);
+      }
+    }
+    return;
+  }
   const float *p1 = tb.TI + ((size_t)min(b0, tb.BI - 1) * tb.NS + j) * out + 2 * op0;
   const float *p2 = tb.TP ? tb.TP + ((size_t)j * tb.BF + max(b0 - tb.BI, 0)) * out + 2 * op0 : p1;
 #pragma unroll
@@ -109,47 +126,35 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
               const float *__restrict__ e2_val, float *__restrict__ msg, int ms, int GS, int HS, int CSP) {
   extern __shared__ __align__(16) float smem[];
   float *comp_s = smem;                                             // [R][CSP]
-  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)R * CSP);    // [warps][2][TPW*LT] (rel, val), double buffered
+  int2 *meta = reinterpret_cast<int2 *>(smem + (size_t)R * CSP);    // [warps][TPW*LT] (rel, val)
   fill_comp(comp_s, compI, compF, R, tb.BI, tb.BF, CSP);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Geo g(GS, HS, lane);
   const int out = tb.out;
-  int2 *tmeta = meta + ((size_t)warp * 2 * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task, buffer 0
-  const int bufstride = g.TPW * LT;
+  int2 *tmeta = meta + ((size_t)warp * g.TPW + (g.lane_on ? g.tslot : 0)) * LT;   // this lane's task
   const float *cbase = comp_s + g.hs * BPT;
   const int n_items = (n_tasks + g.TPW - 1) / g.TPW;
   const bool writer = g.hs == 0 && g.lane_on;
   const int stride = gridDim.x * kTabWarps;
-  auto stage = [&](int buf, const int4 &ti) {      // this lane's share of its task's metadata, asynchronously
-    int2 *dst = tmeta + buf * bufstride;
-    for (int s = g.within; s < ti.z; s += g.LPT) {
-      cp4(&dst[s].x, e2_rel + ti.y + s);
-      cp4(&dst[s].y, e2_val + ti.y + s);
-    }
-    cp_async_commit();
-  };
   int wi = blockIdx.x * kTabWarps + warp;
+  // 16-byte task descriptors {source, first edge, edges}, fetched one item ahead
   int4 cur = ld_task(tasks, wi * g.TPW + g.tslot, n_tasks, g.lane_on && wi < n_items);
-  int4 nxt = ld_task(tasks, (wi + stride) * g.TPW + g.tslot, n_tasks, g.lane_on && wi + stride < n_items);
-  stage(0, cur);
-  for (int it = 0; wi < n_items; wi += stride, ++it) {
-    // task descriptors two items ahead, metadata one item ahead, table rows of this item: all in flight together
-    const int4 nn = ld_task(tasks, (wi + 2 * stride) * g.TPW + g.tslot, n_tasks, g.lane_on && wi + 2 * stride < n_items);
-    stage((it + 1) & 1, nxt);
-    const bool on = cur.z > 0;
+  for (; wi < n_items; wi += stride) {
+    const int4 nxt = ld_task(tasks, (wi + stride) * g.TPW + g.tslot, n_tasks, g.lane_on && wi + stride < n_items);
     const int len = cur.z;
+    __syncwarp();                              // previous item done with the metadata
+    for (int s = g.within; s < len; s += g.LPT)
+      tmeta[s] = make_int2(ldg_stream(e2_rel + cur.y + s), __float_as_int(ldg_stream(e2_val + cur.y + s)));
     float2 T[BPT][NOP];
-    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, cur.x, g.op0, on);
-    cp_async_wait<1>();
+    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, cur.x, g.op0, len > 0);
     __syncwarp();
-    const int2 *mbuf = tmeta + (it & 1) * bufstride;
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
     float *mrow = msg + (size_t)cur.y * ms + 2 * g.op0;
-    for (int s = 0; s < maxlen; ++s, mrow += ms) {
-      const bool live = s < len;
+    // one edge of the task per step: comp row of its relation (16-byte shared loads) against the register-resident rows
+    auto edge = [&](int s, bool live) {
       int2 m = make_int2(0, 0);
-      if (live) m = mbuf[s];
+      if (live) m = tmeta[s];
       const float *cr = cbase + m.x * CSP;
       float2 acc[NOP], acc1[NOP];   // two chains per output pair (even / odd groups of four bases), added at the end
 #pragma unroll
@@ -187,16 +192,20 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
       if (live && writer) {
         // rows are padded to `ms` floats; the pad columns are never read into a stored sum (agg kernels) and stay unwritten
         const float v = __int_as_float(m.y);
+        float *row = mrow + (size_t)s * ms;
 #pragma unroll
         for (int q = 0; q < NOP; ++q)
-          if (NOP == 1 || 2 * (g.op0 + 32 * q) < out) *reinterpret_cast<float2 *>(mrow + 64 * q) = make_float2(v * acc[q].x, v * acc[q].y);
+          if (NOP == 1 || 2 * (g.op0 + 32 * q) < out) *reinterpret_cast<float2 *>(row + 64 * q) = make_float2(v * acc[q].x, v * acc[q].y);
       }
+    };
+    int s = 0;
+    for (; s + 1 < maxlen; s += 2) {      // two edges per trip: their shared-memory loads and FMA chains interleave
+      edge(s, s < len);
+      edge(s + 1, s + 1 < len);
     }
-    __syncwarp();      // the buffer just read is re-staged by the next iteration
+    if (s < maxlen) edge(s, s < len);
     cur = nxt;
-    nxt = nn;
   }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -519,7 +528,7 @@ int launch_tab_msg_fwd(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const flo
   if (pl->n_tasks == 0) return 0;
   TabTables tb{TI, TP, BI, BF, out, (int64_t)g->NS};
   const int LPT = geo.GS > 32 ? 32 : geo.GS * geo.HS, TPW = 32 / LPT;
-  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * 2 * TPW * LT * sizeof(int2);
+  const size_t smem = ((size_t)g->R * geo.CSP) * 4 + (size_t)kTabWarps * TPW * LT * sizeof(int2);
   MRGCN_REQUIRE(smem <= 110 * 1024, MRGCN_E_NOTSUP, "tab_msg_fwd: R*B too large for shared memory (%zu B)", smem);
   const int ms = msg_stride(out);
   const int64_t items = cdiv(pl->n_tasks, TPW);
@@ -594,6 +603,17 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
 
 // bit 0: tab_msg_fwd, bit 1: tab_bwd_w (both need B_I + B_F resp. B_I bases to fit the lane geometry),
 // bit 2: tab_bwd_c (no E x B scratch: `cbuf` then holds the n_pieces x B records)
+// MRGCN_TAB=<mask> in the environment selects the table-term kernels (bit 0 messages, 1 basis gradient, 2 comp gradient).
+// Default 1: measured on AM (profiles/r02_experiments.md) the message kernel + projection beat the round-1 forward by
+// 0.7 ms, while the register-resident backward kernels (2.5 + 3.8 ms) lose to the tile-staging ones (1.8 + 2.8 ms), whose
+// per-lane gathers keep far more loads in flight; they stay available for A/B runs and for the parity tests.
+static int g_tab_mask = -1;
+static int tab_env_mask() {
+  if (g_tab_mask < 0) { const char *e = getenv("MRGCN_TAB"); g_tab_mask = e ? atoi(e) : 1; }
+  return g_tab_mask;
+}
+extern "C" void mrgcn_set_tab_mask(int32_t mask) { g_tab_mask = mask; }
+
 extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
   mrgcn::TabGeom geo;
   int m = 0;
@@ -601,5 +621,5 @@ extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
   if (BI > 0 && mrgcn::tab_geometry(BI, out, geo, mrgcn::kBwdWBpt)) m |= 2;
   int BC, OP;
   if (BI > 0 && mrgcn::tab_c_geometry(BI, out, BC, OP)) m |= 4;
-  return m;
+  return m & tab_env_mask();
 }

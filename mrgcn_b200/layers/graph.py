@@ -19,9 +19,8 @@ def _empty(n, like_dev):
 
 
 def _tab_mode(B, out_dim):
-    """Which table-term kernels (csrc/tab.cu) apply; MRGCN_TAB=0 selects the tile-staging kernels of round 1 (A/B runs)."""
-    if os.environ.get("MRGCN_TAB", "1") == "0":
-        return 0
+    """Which table-term kernels (csrc/tab.cu) apply (bit 0 messages, 1 basis gradient, 2 comp gradient); MRGCN_TAB=<mask>
+    in the environment restricts them to compare against the tile-staging kernels of round 1."""
     return int(nv.lib().mrgcn_tab_mode(B, 0, out_dim))
 
 

@@ -99,6 +99,16 @@ def test_c3_am_shape():
     _nc_case("am", pick_scale("am", [1.0 / 8, 1.0 / 16, 1.0 / 32, 1.0 / 64], 7))
 
 
+def test_c3_am_shape_all_table_kernels():
+    """The same shape (at 1/32) with the register-resident backward kernels switched on (MRGCN_TAB=7)."""
+    from mrgcn_b200 import _native as nv
+    nv.lib().mrgcn_set_tab_mask(7)
+    try:
+        _nc_case("am", 1.0 / 32)
+    finally:
+        nv.lib().mrgcn_set_tab_mask(-1)
+
+
 def _lp_case(shape, scale, n_pos=500, n_rank=60):
     """Link prediction step (link_prediction.py:244-326): encoder (1 layer, ReLU) + DistMult on positives and in-batch
     negatives + BCE; gradients of every parameter; raw and filtered ranks."""
