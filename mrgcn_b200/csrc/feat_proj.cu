@@ -96,6 +96,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 32-byte global store (sm_100: 256-bit accesses): one whole sector per lane and instruction
+__device__ __forceinline__ void st_global_v8(float *p, const float *v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Vt_hi / Vt_lo [NCpad][KP]: row c = b*out + o holds V[b, 0:in, o] (K-major), split into two tf32 pieces; zero padding
@@ -197,9 +203,17 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       const int64_t j = (int64_t)t * BM + warp * 32 + lane;
       if (j < N) {
         float *row = P + j * NC + (size_t)chunk * NB;
+        // a lane owns 4*NB contiguous bytes of its row: whole 32-byte sectors per store when the row pieces are 32-byte
+        // aligned (half-sector 16-byte stores from 32 different rows were the limiter: stall lg_throttle, r02m profile)
+        if ((NC & 7) == 0) {
 #pragma unroll
-        for (int c = 0; c < NB; c += 4)
-          if (chunk * NB + c < NC) *reinterpret_cast<float4 *>(row + c) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+          for (int c = 0; c < NB; c += 8)
+            if (chunk * NB + c < NC) st_global_v8(row + c, d + c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < NB; c += 4)
+            if (chunk * NB + c < NC) *reinterpret_cast<float4 *>(row + c) = make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]);
+        }
       }
     }
   } else if (warp == 4) {

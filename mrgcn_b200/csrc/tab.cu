@@ -85,11 +85,12 @@ __device__ __forceinline__ float2 ld2(const float *p, bool second) {
 // The BPT table rows (x NOP output pairs) of one lane: bases [b0, b0 + BPT) of source j, the first n1 of them from the
 // basis-major identity table, the rest from the node-major projection; everything beyond Btot or `out` is zero.
 // The two common cases - all of the lane's bases in ONE table - walk a pointer (two instructions per load).
+// Lanes without a task pass j = 0: they load (valid) rows they never use, so that the whole warp takes the same path.
 template <int BPT, int NOP, bool EVEN>
-__device__ __forceinline__ void load_rows(float2 (&T)[BPT][NOP], const TabTables &tb, int b0, int64_t j, int op0, bool on) {
+__device__ __forceinline__ void load_rows(float2 (&T)[BPT][NOP], const TabTables &tb, int b0, int64_t j, int op0) {
   const int out = tb.out, Btot = tb.BI + tb.BF;
   const int n1 = min(max(tb.BI - b0, 0), BPT);
-  const int nvalid = on ? min(max(Btot - b0, 0), BPT) : 0;
+  const int nvalid = min(max(Btot - b0, 0), BPT);
   const size_t s1 = (size_t)tb.NS * out;
   const bool o_ok = NOP > 1 || 2 * op0 < out;
   if (nvalid == BPT && o_ok && (n1 == BPT || n1 == 0)) {
@@ -147,7 +148,7 @@ k_tab_msg_fwd(TabTables tb, const float *__restrict__ compI, const float *__rest
     for (int s = g.within; s < len; s += g.LPT)
       tmeta[s] = make_int2(ldg_stream(e2_rel + cur.y + s), __float_as_int(ldg_stream(e2_val + cur.y + s)));
     float2 T[BPT][NOP];
-    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, cur.x, g.op0, len > 0);
+    load_rows<BPT, NOP, EVEN>(T, tb, g.hs * BPT, cur.x, g.op0);
     __syncwarp();
     const int maxlen = __reduce_max_sync(0xffffffffu, len);
     float *mrow = msg + (size_t)cur.y * ms + 2 * g.op0;
