@@ -243,6 +243,25 @@ int mrgcn_distmult_rank(const int64_t *facts /* [F,3] */, int64_t F, int32_t hea
                         const int32_t *filt_ptr, const int32_t *filt_idx, /* NULL = raw */
                         float *scores_ws /* [F*N] workspace */, int64_t *rank, mrgcn_stream_t stream);
 
+/* ---- either side of the path ------------------------------------------------------------------
+ * Fused gradient clipping + Adam.  Replaces, for CUDA parameters, the pair
+ *   nn.utils.clip_grad_norm_(model.parameters(), max_norm); optimizer.step()        (torch.optim.Adam, no amsgrad)
+ * of mrgcn/tasks/node_classification.py:190-193 / link_prediction.py:324-326 (optimizer built in mrgcn/tasks/utils.py:8-45).
+ * mrgcn_grad_sqnorm: total[0] (+)= sum g^2 (double; ws: mrgcn_sqnorm_ws_elems() doubles); call once per gradient tensor
+ * with accumulate = 0 for the first.  mrgcn_adam_clip: one pass over p, g, m, v with
+ *   coef = min(1, max_norm / (sqrt(total_sq[0]) + 1e-6))   (max_norm <= 0 or total_sq NULL: no clipping)
+ * `step` is the 1-based step count of the bias corrections. */
+int64_t mrgcn_sqnorm_ws_elems(void);
+int mrgcn_grad_sqnorm(const float *g, int64_t n, double *ws, double *total, int32_t accumulate, mrgcn_stream_t stream);
+int mrgcn_adam_clip(float *p, const float *g, float *m, float *v, int64_t n, const double *total_sq, float max_norm,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, mrgcn_stream_t stream);
+/* Gated scatter of one modality's encoder output into the node-feature matrix (mrgcn/models/mrgcn.py:295-301):
+ *   X[row_idx[i], col0 : col0 + d] = gate[0] * src[i, :]        and its backward (g_src, g_gate; ws as above). */
+int mrgcn_scatter_rows(const float *src, const int64_t *row_idx, const float *gate, float *X, int64_t m, int32_t d,
+                       int32_t ldx, int32_t col0, mrgcn_stream_t stream);
+int mrgcn_scatter_rows_bwd(const float *gX, const int64_t *row_idx, const float *gate, const float *src, float *g_src,
+                           float *g_gate, double *ws, int64_t m, int32_t d, int32_t ldx, int32_t col0, mrgcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

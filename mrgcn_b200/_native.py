@@ -99,6 +99,14 @@ SYMBOLS = {
     "mrgcn_upload_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "mrgcn_rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), C.c_void_p]),
     "mrgcn_rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), C.c_void_p]),
+    "mrgcn_sqnorm_ws_elems": (C.c_int64, []),
+    "mrgcn_grad_sqnorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mrgcn_adam_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
+    "mrgcn_scatter_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p]),
+    "mrgcn_scatter_rows_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mrgcn_distmult_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
     "mrgcn_distmult_bwd_ws_elems": (C.c_int64, [C.c_int64]),

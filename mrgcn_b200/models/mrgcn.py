@@ -153,7 +153,7 @@ class MRGCN(nn.Module):
         if self.compute_modality_embeddings:
             batch_idx = torch.arange(self.num_nodes) if outer_idx is None else torch.as_tensor(outer_idx)
             XF = self._compute_modality_embeddings(F, batch_idx)
-            X = torch.as_tensor(X).to(self.X_device)
+            X = torch.as_tensor(X).to(XF.device)
             X_dev = torch.cat([X.to(XF.dtype), XF], dim=1).to(rgcn_device)           # mrgcn.py:199-204
         elif not self.rgcn.layers["layer_0"].featureless and not self.partitioned:
             # extension: pre-computed node features handed over as batch.X[0] (BASELINE.json config 3);
@@ -192,7 +192,9 @@ class MRGCN(nn.Module):
 
     def _compute_modality_embeddings(self, F, batch_idx):
         """mrgcn.py:250-305: gate * encoder(data) scattered into the rows of the nodes that carry the modality."""
-        dev = self.X_device
+        # the feature matrix is assembled where the relational part lives: every modality block is written by one fused
+        # gate-scale + row-scatter kernel (mrgcn_b200/optim.py: gated_scatter) instead of mul + masked assignment
+        dev = self.devices["relational"] if self.devices["relational"].type == "cuda" else self.X_device
         X = torch.zeros((len(batch_idx), self.modality_out_dim), dtype=torch.float32, device=dev)
         batch_idx = torch.as_tensor(batch_idx)
         offset = 0
@@ -219,7 +221,11 @@ class MRGCN(nn.Module):
                 else:
                     data = enc[F_mask].float()
                 out = module(data.to(mod_dev))
-                out = torch.mul(out, self.gate_weights[i_gate].to(out.device))
-                X[X_mask.to(dev), offset:offset + out_dim] = out.to(dev)
+                if dev.type == "cuda":
+                    from ..optim import gated_scatter
+                    X = gated_scatter(X, out, torch.nonzero(X_mask).flatten(), self.gate_weights[i_gate], offset)
+                else:
+                    out = torch.mul(out, self.gate_weights[i_gate].to(out.device))
+                    X[X_mask.to(dev), offset:offset + out_dim] = out.to(dev)
                 offset += out_dim
         return X
