@@ -24,7 +24,8 @@
 //   warp 5      MMA issuer (one thread) and TMEM owner: D[tmem] += A[tmem] . B[smem]
 //   warps 0-3   epilogue: tcgen05.ld the 4 partial accumulators, add, release TMEM, store P rows (node-major)
 // mbarrier rings: raw_full (TMA tx) / raw_empty (4 converter warps), a_full (4 converter warps) / a_empty (tcgen05.commit),
-// tmem_full / tmem_empty.  TMEM columns: 4 x NB accumulators + 3 x 64 operand stages <= 512.
+// tmem_full / acc_free[3] (the epilogue hands every accumulator back as soon as it has read it).  TMEM columns: 4 x NB
+// accumulators + 3 x 64 operand stages <= 512.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -102,6 +103,19 @@ __device__ __forceinline__ void st_global_v8(float *p, const float *v) {
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                : "memory");
 }
+// one lane of a converged warp (warp-uniform control flow around it keeps the operands in uniform registers: a
+// `lane == 0` branch makes the compiler wrap every tcgen05 / TMA instruction in an elect-and-broadcast loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Vt_hi / Vt_lo [NCpad][KP]: row c = b*out + o holds V[b, 0:in, o] (K-major), split into two tf32 pieces; zero padding
@@ -149,8 +163,8 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   unsigned char *a_raw = b_lo + (size_t)NKC * B_TILE;      // [RS][128 rows][128 B] raw fp32, 128B-swizzled by the TMA
   uint64_t *bars = reinterpret_cast<uint64_t *>(a_raw + (size_t)RS * A_TILE);
   uint64_t *raw_full = bars, *raw_empty = bars + RS, *a_full = bars + 2 * RS, *a_empty = a_full + AS, *b_full = a_empty + AS,
-           *tmem_full = b_full + 1, *tmem_empty = b_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 3);
+           *tmem_full = b_full + 1, *acc_free = b_full + 2;      // acc_free[0]: correction + main 0, [1]: main 1, [2]: main 2
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 5);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % NCH, rg = blockIdx.x / NCH, GR = gridDim.x / NCH;
   const int n_my = rg < n_row_tiles ? (n_row_tiles - rg + GR - 1) / GR : 0;
@@ -160,7 +174,8 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-    mbar_init(b_full, 1); mbar_init(tmem_full, 1); mbar_init(tmem_empty, 4);
+    mbar_init(b_full, 1); mbar_init(tmem_full, 1);
+    for (int s = 0; s < 3; ++s) mbar_init(&acc_free[s], 4);
     mbar_fence_init();
   }
   if (warp == 5) {
@@ -179,27 +194,35 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
       mbar_wait(tmem_full, it & 1, 1, 64);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+      // accumulator-major: the correction terms and main 0 first - the next tile's MMAs start on exactly those - and
+      // each accumulator is handed back as soon as it has been read, so that the MMAs restart under the rest of the read
       float d[NB];
+      {
+        uint32_t r[NB / 16][16];
 #pragma unroll
-      for (int cb = 0; cb < NB / 16; ++cb) {
-        uint32_t r[4][16];
-        tmem_ld16(t0 + NG * NB + cb * 16, r[3]);           // correction terms (smallest) first
-#pragma unroll
-        for (int gq = 0; gq < 3; ++gq)
-          if (gq < NG) tmem_ld16(t0 + gq * NB + cb * 16, r[gq]);
+        for (int cb = 0; cb < NB / 16; ++cb) tmem_ld16(t0 + NG * NB + cb * 16, r[cb]);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v = __uint_as_float(r[3][i]);
+        for (int cb = 0; cb < NB / 16; ++cb)
 #pragma unroll
-          for (int gq = 0; gq < 3; ++gq)
-            if (gq < NG) v += __uint_as_float(r[gq][i]);
-          d[cb * 16 + i] = v;
-        }
+          for (int i = 0; i < 16; ++i) d[cb * 16 + i] = __uint_as_float(r[cb][i]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_one(tmem_empty);           // TMEM free: the next tile's MMAs overlap the stores below
+#pragma unroll
+      for (int gq = 0; gq < 3; ++gq) {
+        if (gq < NG) {
+          uint32_t r[NB / 16][16];
+#pragma unroll
+          for (int cb = 0; cb < NB / 16; ++cb) tmem_ld16(t0 + gq * NB + cb * 16, r[cb]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cb = 0; cb < NB / 16; ++cb)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[cb * 16 + i] += __uint_as_float(r[cb][i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_one(&acc_free[gq]);
+      }
       const int64_t j = (int64_t)t * BM + warp * 32 + lane;
       if (j < N) {
         float *row = P + j * NC + (size_t)chunk * NB;
@@ -218,50 +241,67 @@ k_feat_proj(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     }
   } else if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(b_full, (uint32_t)(2 * NKC * B_TILE));
       for (int kc = 0; kc < NKC; ++kc) {
         tma_load_2d(b_hi + (size_t)kc * B_TILE, &tmVhi, kc * 32, chunk * NB, b_full);
         tma_load_2d(b_lo + (size_t)kc * B_TILE, &tmVlo, kc * 32, chunk * NB, b_full);
       }
-      int ks = 0;
-      for (int it = 0; it < n_my; ++it) {
-        const int t = rg + it * GR;
-        for (int kc = 0; kc < NKC; ++kc, ++ks) {
-          const int s = ks % RS;
-          mbar_wait(&raw_empty[s], ((ks / RS) & 1) ^ 1, 2, 32);
+    }
+    __syncwarp();
+    int ks = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int t = rg + it * GR;
+      for (int kc = 0; kc < NKC; ++kc, ++ks) {
+        const int s = ks % RS;
+        mbar_wait(&raw_empty[s], ((ks / RS) & 1) ^ 1, 2, 32);
+        if (elect_one()) {
           mbar_expect_tx(&raw_full[s], A_TILE);
           tma_load_2d(a_raw + (size_t)s * A_TILE, &tmX, kc * 32, t * BM, &raw_full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for the compiler
       mbar_wait(b_full, 0, 3);
+      // ONE lane issues every MMA of the CTA and its instruction stream is the critical path: the first versions branched
+      // on `lane == 0` (every MMA then sits in an elect-and-broadcast loop) and rebuilt both 64-bit descriptors per MMA,
+      // ~1100 issue cycles for a 480-cycle stage (profiles/r02m_*).  Here the whole warp runs the loop, one elected lane
+      // issues, and the B descriptors - which differ only in their 14-bit start address - are advanced by constants.
+      const uint64_t dbh_base = desc_k_sw128(smem_u32(b_hi)), dbl_base = desc_k_sw128(smem_u32(b_lo));
+      const uint32_t d_corr = tb + NG * NB;
       int ks = 0;
       for (int it = 0; it < n_my; ++it) {
-        mbar_wait(tmem_empty, (it & 1) ^ 1, 4);
-        tc_fence_after();
-        const uint32_t d_corr = tmem_base + NG * NB;
         for (int kc = 0; kc < NKC; ++kc, ++ks) {
+          if ((kc & 1) == 0) {      // first use of main accumulator kc/2 (and, at kc = 0, of the correction accumulator)
+            mbar_wait(&acc_free[kc >> 1], (it & 1) ^ 1, 4);
+          }
           const int s = ks % AS;
           mbar_wait(&a_full[s], (ks / AS) & 1, 5);
           tc_fence_after();
-          const uint32_t a_hi = tmem_base + A_COL0 + s * 64, a_lo = a_hi + 32;
-          const uint32_t bh = smem_u32(b_hi + (size_t)kc * B_TILE), bl = smem_u32(b_lo + (size_t)kc * B_TILE);
-          const uint32_t d_main = tmem_base + (kc >> 1) * NB;
+          const uint32_t a_hi = tb + A_COL0 + s * 64, a_lo = a_hi + 32;
+          const uint64_t dbh = dbh_base + (uint64_t)((kc * B_TILE) >> 4), dbl = dbl_base + (uint64_t)((kc * B_TILE) >> 4);
+          const uint32_t d_main = tb + (kc >> 1) * NB;
+          if (elect_one()) {
+            // 4 K steps of 8 tf32: 8 TMEM columns of A, 32 bytes (2 descriptor units) of every B row
+            mma_tf32_ts(d_main, a_hi, dbh, idesc, kc & 1);
+            mma_tf32_ts(d_corr, a_lo, dbh, idesc, kc);
+            mma_tf32_ts(d_corr, a_hi, dbl, idesc, 1);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {     // 4 K steps of 8 tf32: 8 TMEM columns of A, 32 bytes of every B row
-            const uint64_t dbh = desc_k_sw128(bh + j * 32), dbl = desc_k_sw128(bl + j * 32);
-            mma_tf32_ts(d_main, a_hi + j * 8, dbh, idesc, ((kc & 1) | j) != 0);
-            mma_tf32_ts(d_corr, a_lo + j * 8, dbh, idesc, (kc | j) != 0);
-            mma_tf32_ts(d_corr, a_hi + j * 8, dbl, idesc, 1);
+            for (int j = 1; j < 4; ++j) {
+              mma_tf32_ts(d_main, a_hi + j * 8, dbh + 2 * j, idesc, 1);
+              mma_tf32_ts(d_corr, a_lo + j * 8, dbh + 2 * j, idesc, 1);
+              mma_tf32_ts(d_corr, a_hi + j * 8, dbl + 2 * j, idesc, 1);
+            }
+            tc_commit(&a_empty[s]);        // operand stage free once these MMAs have read it
+            if (kc == NKC - 1) tc_commit(tmem_full);      // all accumulators of the tile complete
           }
-          tc_commit(&a_empty[s]);        // operand stage free once these MMAs have read it
+          __syncwarp();
         }
-        tc_commit(tmem_full);            // all accumulators of the tile complete
       }
     }
   } else {
