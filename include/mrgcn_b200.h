@@ -120,7 +120,8 @@ typedef struct mrgcn_tab_plan {
 /* which table-term kernels apply to (B_I identity bases, B_F projected feature bases, out): bit 0 forward messages,
  * bit 1 basis gradient, bit 2 comp gradient without the E x B scratch (cbuf then holds n_pieces x B records). */
 int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out);
-/* Which of them may be used at all (same bits; -1 = re-read MRGCN_TAB from the environment, default 1: messages only). */
+/* Force the choice (same bits); -1 = automatic by shape: messages always, basis gradient for out >= 64 (csrc/tab.cu).
+ * MRGCN_TAB=<mask> in the environment forces it at start-up. */
 void mrgcn_set_tab_mask(int32_t mask);
 
 /* Re-emit the reference's stacked adjacency as E1/E2/E3.
@@ -233,15 +234,18 @@ int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int64_t *o, int
                        int64_t N, int64_t NR, int32_t h, float *gE, float *gRel, int32_t *ws,
                        mrgcn_stream_t stream);
 
-/* Ranking.  Replaces compute_ranks_fast + filter_scores_ (link_prediction.py:557-643) for one side:
- *   scores[f,c] = sum_k E[c,k]*Rel[p_f,k]*E[fixed_f,k]  over all candidates c in [0,N)
- *   entries listed in filt (CSR over facts: filt_ptr[f..f+1] -> candidate ids) are set to -inf
+/* Ranking.  Replaces compute_ranks_fast + filter_scores_ (link_prediction.py:557-643) for one side, in GEMM form
+ * (csrc/rank.cu): 32-fact x 128-candidate score tiles in registers, compared with the target's score on the fly - no
+ * F x N score matrix.
+ *   scores[f,c] = sum_k (E[s,k]*Rel[p_f,k])*E[o,k]  with the candidate c in the subject (head=1) or object (head=0) slot
+ *   candidates listed in filt (CSR over facts: filt_ptr[f..f+1] -> candidate ids; the target itself is ignored) do not count
  *   rank[f] = #(scores[f,:] > scores[f,target_f]) + round_half_even((#ties-1)/2) + 1
- * head=1: candidates replace the subject (fixed = object), head=0: candidates replace the object. */
+ * ws: mrgcn_distmult_rank_ws_elems(F) int32 words. */
+int64_t mrgcn_distmult_rank_ws_elems(int64_t F);
 int mrgcn_distmult_rank(const int64_t *facts /* [F,3] */, int64_t F, int32_t head,
                         const float *E, const float *Rel, int64_t N, int32_t h,
                         const int32_t *filt_ptr, const int32_t *filt_idx, /* NULL = raw */
-                        float *scores_ws /* [F*N] workspace */, int64_t *rank, mrgcn_stream_t stream);
+                        int32_t *ws, int64_t *rank, mrgcn_stream_t stream);
 
 /* ---- either side of the path ------------------------------------------------------------------
  * Fused gradient clipping + Adam.  Replaces, for CUDA parameters, the pair

@@ -88,72 +88,6 @@ k_distmult_bwd_rels(const int32_t *__restrict__ keys, const int32_t *__restrict_
   }
 }
 
-// ---- ranking -------------------------------------------------------------------------------------
-// scores[f, c] for all candidates c; one warp per (fact, candidate), the fact's fixed row and relation row
-// are staged in shared memory.  Operand order of the products follows score_distmult_bc: (s*p)*o.
-__global__ void __launch_bounds__(kThreads)
-k_rank_scores(const int64_t *__restrict__ facts, int head, const float *__restrict__ E, const float *__restrict__ Rel,
-              int64_t N, int h, float *__restrict__ scores) {
-  extern __shared__ float q[];  // [2][h]: relation row, fixed entity row
-  const int64_t f = blockIdx.y;
-  const int64_t pf = facts[3 * f + 1], fixed = head ? facts[3 * f + 2] : facts[3 * f];
-  for (int k = threadIdx.x; k < h; k += kThreads) {
-    q[k] = Rel[(size_t)pf * h + k];
-    q[h + k] = E[(size_t)fixed * h + k];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t c0 = (int64_t)blockIdx.x * 64;
-  for (int64_t c = c0 + warp; c < min(N, c0 + 64); c += kThreads / 32) {
-    const float *ec = E + (size_t)c * h;
-    float acc = 0.f;
-    if (head) for (int k = lane; k < h; k += 32) acc = fmaf(ec[k] * q[k], q[h + k], acc);
-    else      for (int k = lane; k < h; k += 32) acc = fmaf(q[h + k] * q[k], ec[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) scores[(size_t)f * N + c] = acc;
-  }
-}
-
-__global__ void k_rank_filter(const int64_t *__restrict__ facts, int head, const int32_t *__restrict__ fptr,
-                              const int32_t *__restrict__ fidx, int64_t N, float *__restrict__ scores) {
-  const int64_t f = blockIdx.x;
-  const int64_t target = head ? facts[3 * f] : facts[3 * f + 2];
-  for (int x = fptr[f] + threadIdx.x; x < fptr[f + 1]; x += blockDim.x) {
-    int c = fidx[x];
-    if (c != target) scores[(size_t)f * N + c] = -INFINITY;   // link_prediction.py:566,572
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_rank_count(const int64_t *__restrict__ facts, int head, int64_t N, const float *__restrict__ scores,
-             int64_t *__restrict__ rank) {
-  __shared__ int gt_s[kThreads], eq_s[kThreads];
-  const int64_t f = blockIdx.x;
-  const int64_t target = head ? facts[3 * f] : facts[3 * f + 2];
-  const float *sf = scores + (size_t)f * N;
-  const float tv = sf[target];
-  int gt = 0, eq = 0;
-  for (int64_t c = threadIdx.x; c < N; c += kThreads) {
-    float v = sf[c];
-    gt += v > tv;
-    eq += v == tv;
-  }
-  gt_s[threadIdx.x] = gt; eq_s[threadIdx.x] = eq;
-  __syncthreads();
-  for (int s = kThreads / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) { gt_s[threadIdx.x] += gt_s[threadIdx.x + s]; eq_s[threadIdx.x] += eq_s[threadIdx.x + s]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    // rank = #greater + round_half_even((#ties - 1) / 2) + 1      (link_prediction.py:632-643)
-    int64_t m = (int64_t)eq_s[0] - 1;
-    int64_t half = m / 2;
-    if (m > 0 && (m & 1) && (half & 1)) half += 1;
-    if (m < 0) half = 0;  // target itself NaN: no tie with itself; torch.round(-0.5) = -0 -> 0
-    rank[f] = gt_s[0] + half + 1;
-  }
-}
-
 static int sort_i32(int32_t *kin, int32_t *kout, int32_t *vin, int32_t *vout, int64_t m, cudaStream_t st) {
   size_t bytes = 0;
   MRGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, 32, st));
@@ -210,26 +144,5 @@ extern "C" int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int6
   k_distmult_bwd_rels<<<(unsigned)cdiv(n * 32, kThreads), kThreads, 0, st>>>(pko, pvo, n, s, o, gscore, E, h, gRel);
     MRGCN_LAUNCH_CHECK();
   }
-  return 0;
-}
-
-extern "C" int mrgcn_distmult_rank(const int64_t *facts, int64_t F, int32_t head, const float *E, const float *Rel,
-                                   int64_t N, int32_t h, const int32_t *filt_ptr, const int32_t *filt_idx,
-                                   float *scores_ws, int64_t *rank, mrgcn_stream_t stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  MRGCN_REQUIRE(F >= 0 && N > 0 && h > 0 && scores_ws && rank, MRGCN_E_BADARG, "distmult_rank: bad arguments");
-  MRGCN_REQUIRE(F < 65536, MRGCN_E_BADARG, "distmult_rank: at most 65535 facts per call");
-  if (F == 0) return 0;
-  dim3 grid((unsigned)cdiv(N, 64), (unsigned)F);
-  MRGCN_PROF("rank_scores");
-  k_rank_scores<<<grid, kThreads, 2 * h * sizeof(float), st>>>(facts, head, E, Rel, N, h, scores_ws);
-  MRGCN_LAUNCH_CHECK();
-  if (filt_ptr && filt_idx) {
-    k_rank_filter<<<(unsigned)F, 128, 0, st>>>(facts, head, filt_ptr, filt_idx, N, scores_ws);
-    MRGCN_LAUNCH_CHECK();
-  }
-  MRGCN_PROF("rank_count");
-  k_rank_count<<<(unsigned)F, kThreads, 0, st>>>(facts, head, N, scores_ws, rank);
-  MRGCN_LAUNCH_CHECK();
   return 0;
 }

@@ -604,16 +604,18 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
 
 // bit 0: tab_msg_fwd, bit 1: tab_bwd_w (both need B_I + B_F resp. B_I bases to fit the lane geometry),
 // bit 2: tab_bwd_c (no E x B scratch: `cbuf` then holds the n_pieces x B records)
-// MRGCN_TAB=<mask> in the environment selects the table-term kernels (bit 0 messages, 1 basis gradient, 2 comp gradient).
-// Default 1: measured on AM (profiles/r02_experiments.md) the message kernel + projection beat the round-1 forward by
-// 0.7 ms, while the register-resident backward kernels (2.5 + 3.8 ms) lose to the tile-staging ones (1.8 + 2.8 ms), whose
-// per-lane gathers keep far more loads in flight; they stay available for A/B runs and for the parity tests.
-static int g_tab_mask = -1;
+// MRGCN_TAB=<mask> in the environment (or mrgcn_set_tab_mask) forces the table-term kernels; without it the choice is by
+// shape, from measurements (profiles/r02_experiments.md):
+//   bit 0 always - the message kernel + projection beat the round-1 forward on every shape;
+//   bit 1 for wide outputs (out >= 64) - on the FB15k-237 layer (out 200, 2 bases) tab_bwd_w takes 0.09 ms where the
+//         tile-staging ident_bwd_w takes 1.9 ms; on AM (out 10, 40 bases) it loses 2.5 ms to 1.8 ms;
+//   bit 2 never by default - tab_bwd_c ties on FB15k-237 (0.76 ms both) and loses on AM (3.8 ms vs 2.2 + 0.5 ms).
+static int g_tab_mask = -1;      // -1: not read yet, -2: automatic
 static int tab_env_mask() {
-  if (g_tab_mask < 0) { const char *e = getenv("MRGCN_TAB"); g_tab_mask = e ? atoi(e) : 1; }
+  if (g_tab_mask == -1) { const char *e = getenv("MRGCN_TAB"); g_tab_mask = e ? atoi(e) : -2; }
   return g_tab_mask;
 }
-extern "C" void mrgcn_set_tab_mask(int32_t mask) { g_tab_mask = mask; }
+extern "C" void mrgcn_set_tab_mask(int32_t mask) { g_tab_mask = mask < 0 ? -2 : mask; }
 
 extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
   mrgcn::TabGeom geo;
@@ -622,5 +624,6 @@ extern "C" int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out) {
   if (BI > 0 && mrgcn::tab_geometry(BI, out, geo, mrgcn::kBwdWBpt)) m |= 2;
   int BC, OP;
   if (BI > 0 && mrgcn::tab_c_geometry(BI, out, BC, OP)) m |= 4;
-  return m & tab_env_mask();
+  const int forced = tab_env_mask();
+  return m & (forced >= 0 ? forced : (1 | (out >= 64 ? 2 : 0)));
 }

@@ -78,6 +78,26 @@ class A_Batch:
         self.neighbours = [torch.from_numpy(a) for a in self.neighbours]
 
 
+class DeviceABatch(A_Batch):
+    """A_Batch built on the GPU from a device-resident RelGraph (mrgcn_b200.graph): frontier expansion
+    (`getNeighboursSparse`, batch.py:228-243) and row slices (`A[sample_idx]`, :190) are gathers over the destination-major
+    edge order, no Python loop over nodes and no scipy.  Values are truncated to int8 exactly as A_Batch.as_tensors_ does
+    (batch.py:223-226) unless value_dtype says otherwise."""
+
+    def __init__(self, graph, batch_idx, num_layers, value_dtype=torch.int8):
+        self.neighbours, self.row = [], []
+        self.device = graph.device
+        self.node_index = torch.as_tensor(batch_idx, device=graph.device).long()
+        sample = self.node_index
+        for _ in range(num_layers):
+            self.row.append(graph.row_slice(sample, value_dtype))
+            sample = graph.neighbours(sample)
+            self.neighbours.append(sample)
+
+    def as_tensors_(self):
+        pass
+
+
 class MiniBatch(Batch):
     def __init__(self, A=None, X=None, batch_node_idx=None, num_layers=None):
         super().__init__(batch_node_idx)
@@ -102,6 +122,6 @@ def getNeighboursSparse(A, idx):
 
 def getAdjacencyNodeColumnIdx(idx, num_nodes, num_relations):
     """batch.py:245-250 — column ids r*N + i for every relation r and node i in idx (vectorised)."""
-    idx = torch.as_tensor(idx, dtype=torch.int64)
-    rel = torch.arange(num_relations, dtype=torch.int64).view(-1, 1)
+    idx = torch.as_tensor(idx).long()
+    rel = torch.arange(num_relations, dtype=torch.int64, device=idx.device).view(-1, 1)
     return (rel * num_nodes + idx.view(1, -1)).reshape(-1)

@@ -55,6 +55,33 @@ def chunk_worklist(grpptr, R, ch):
     return chunk_rel, chunk_ptr, rel_chunk_ptr, order
 
 
+def chunk_worklist_device(grpptr, R, ch):
+    """`chunk_worklist` with torch ops on the tensor's device (no host round trip of the group pointers: mini-batch
+    mode builds a graph per layer per batch).  Returns int64 tensors (chunk_rel, chunk_ptr, rel_chunk_ptr, order)."""
+    grpptr = grpptr.long()
+    dev = grpptr.device
+    ngrp = grpptr.numel() - 1
+    cnt = grpptr[1:] - grpptr[:-1]
+    nch = (cnt + ch - 1) // ch
+    grp_chunk_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(nch, 0)])
+    chunk_grp = torch.repeat_interleave(torch.arange(ngrp, device=dev), nch)
+    n_chunks = chunk_grp.numel()
+    within = torch.arange(n_chunks, device=dev) - grp_chunk_ptr[chunk_grp]
+    chunk_ptr = torch.cat([grpptr[chunk_grp] + within * ch, grpptr[-1:]])
+    chunk_rel = chunk_grp % R
+    order = torch.argsort(chunk_rel, stable=True)
+    rel_chunk_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(torch.bincount(chunk_rel, minlength=R), 0)])
+    return chunk_rel, chunk_ptr, rel_chunk_ptr, order
+
+
+def hub_segments_device(deg, seg):
+    """`hub_segments` with torch ops on the tensor's device."""
+    d = deg.long()
+    nseg = (d + seg - 1) // seg
+    first = torch.cat([torch.zeros(1, dtype=torch.long, device=d.device), torch.cumsum(nseg, 0)])
+    return torch.repeat_interleave(torch.arange(d.numel(), device=d.device), nseg), first
+
+
 def hub_segments(deg, seg):
     """Hubs (rows / sources with `deg` entries each) cut into segments of `seg` entries: (seg_hub[n], seg_first[h+1])."""
     d = np.asarray(deg, dtype=np.int64)
@@ -177,28 +204,30 @@ class RelGraph:
             setattr(c, name, getattr(self, name).data_ptr())
 
     def _build_worklists(self, chunk=None):
-        """Hub lists and the relation-chunk work list (host side; one sync, at build time only)."""
+        """Hub lists and the relation-chunk work list, computed on the device; the only host traffic is the handful of
+        counts the launches need (one small device -> host copy per graph)."""
         dev = self.device
         deg_r = self.rowptr[1:] - self.rowptr[:-1]
         deg_c = self.colptr[1:] - self.colptr[:-1]
         self.long_rows = torch.nonzero(deg_r > LONG_THRESH).flatten().to(_I32)
         self.long_cols = torch.nonzero(deg_c > LONG_THRESH).flatten().to(_I32)
-        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        one = torch.zeros(1, dtype=_I32, device=dev)
 
         def segments(deg, hubs):
-            hub, first = hub_segments(deg[hubs.long()].cpu().numpy(), LONG_SEG)
-            return mk(hub if len(hub) else [0]), mk(first), int(first[-1])
-        self.row_seg_hub, self.row_seg_first, self.n_row_segs = segments(deg_r, self.long_rows)
-        self.col_seg_hub, self.col_seg_first, self.n_col_segs = segments(deg_c, self.long_cols)
+            hub, first = hub_segments_device(deg[hubs.long()], LONG_SEG)
+            return (hub.to(_I32) if hub.numel() else one), first.to(_I32), first[-1:]
+        self.row_seg_hub, self.row_seg_first, nrs = segments(deg_r, self.long_rows)
+        self.col_seg_hub, self.col_seg_first, ncs = segments(deg_c, self.long_cols)
         ch = chunk or _chunk_size(self.E)
-        chunk_rel, chunk_ptr, rel_chunk_ptr, order = chunk_worklist(self.relptr.cpu().numpy(), self.R, ch)
-        n_chunks = len(chunk_rel)
+        chunk_rel, chunk_ptr, rel_chunk_ptr, order = chunk_worklist_device(self.relptr, self.R, ch)
+        n_chunks = chunk_rel.numel()          # a shape: known on the host without a copy
+        self.n_row_segs, self.n_col_segs = (int(v) for v in torch.cat([nrs, ncs]).tolist())
         self.chunk_size = ch
         self.n_chunks = n_chunks
-        self.chunk_rel = mk(chunk_rel) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
-        self.chunk_ptr = mk(chunk_ptr)
-        self.rel_chunk_ptr = mk(rel_chunk_ptr)
-        self.rel_chunk_idx = mk(order) if n_chunks else torch.zeros(1, dtype=_I32, device=dev)
+        self.chunk_rel = chunk_rel.to(_I32) if n_chunks else one
+        self.chunk_ptr = chunk_ptr.to(_I32)
+        self.rel_chunk_ptr = rel_chunk_ptr.to(_I32)
+        self.rel_chunk_idx = order.to(_I32) if n_chunks else one
         c = self.c
         c.long_rows = self.long_rows.data_ptr() if len(self.long_rows) else None
         c.n_long_rows, c.long_row_thresh = len(self.long_rows), LONG_THRESH
@@ -272,6 +301,31 @@ class RelGraph:
         g = cls.from_coo_arrays(row, col, val, num_nodes, R * num_nodes, R, chunk)
         g.coo = (row, col, val)
         return g
+
+    def _row_edges(self, rows):
+        """E1 positions of the entries of `rows` (device int64), and the local row of every entry."""
+        rows = rows.to(self.device).long()
+        lo = self.rowptr[rows].long()
+        deg = self.rowptr[rows + 1].long() - lo
+        total_first = torch.cumsum(deg, 0) - deg
+        local = torch.repeat_interleave(torch.arange(rows.numel(), device=self.device), deg)
+        pos = torch.arange(local.numel(), device=self.device) - total_first[local] + lo[local]
+        return pos, local
+
+    def row_slice(self, rows, value_dtype=None):
+        """`A[rows]` (mrgcn/data/batch.py:190) as a device sparse COO of shape (len(rows), R*NS), without leaving the GPU.
+        value_dtype=torch.int8 reproduces the truncation of A_Batch.as_tensors_ (batch.py:223-226)."""
+        pos, local = self._row_edges(rows)
+        col = self.e1_rel[pos].long() * self.NS + self.e1_src[pos].long()
+        val = self.e1_val[pos]
+        if value_dtype is not None:
+            val = val.to(value_dtype)
+        return torch.sparse_coo_tensor(torch.stack([local, col]), val, (int(rows.numel()), self.R * self.NS))
+
+    def neighbours(self, rows):
+        """`getNeighboursSparse` (batch.py:228-243) on the device: the sorted set of source nodes of `rows`, any relation."""
+        pos, _ = self._row_edges(rows)
+        return torch.unique(self.e1_src[pos].long())
 
     def tab_plan(self):
         """Work plan of the table-term kernels over this graph's E2 order (built on first use, then cached)."""

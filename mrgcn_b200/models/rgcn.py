@@ -38,7 +38,7 @@ class RGCN(nn.Module):
         nn.init.xavier_uniform_(self.relations)
 
     def forward(self, X, A):
-        if type(A) is A_Batch or type(A).__name__ == "A_Batch":   # ours or the reference's
+        if isinstance(A, A_Batch) or type(A).__name__ == "A_Batch":   # ours (host or device built) or the reference's
             return self._forward_mini_batch(X, A)
         return self._forward_full_batch(X, A)
 

@@ -82,44 +82,67 @@ def truedicts(facts):
     return heads, tails
 
 
-def _filter_csr(data, true_dict, head):
-    ptr, idx = [0], []
-    for s, p, o in np.asarray(data).tolist():
-        idx.extend(true_dict[(p, o)] if head else true_dict[(s, p)])
-        ptr.append(len(idx))
-    return np.asarray(ptr, dtype=np.int32), np.asarray(idx if idx else [0], dtype=np.int32)
+def filter_csr_device(facts, head):
+    """The reference's filter dictionaries (`truedicts` + `filter_scores_`, link_prediction.py:557-591) as a CSR over the
+    facts, built on the device by sort + segment: for fact f the list of all subjects s' with (s', p_f, o_f) in `facts`
+    (head side) or all objects o' with (s_f, p_f, o') in `facts` (tail side).  The target itself stays in the list (the
+    kernel skips it, as filter_scores_ does).  facts: int64 (F, 3) device tensor.  Returns int32 (ptr[F+1], idx)."""
+    F = facts.shape[0]
+    dev = facts.device
+    if F == 0:
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        return z, z
+    a, b = (facts[:, 1], facts[:, 2]) if head else (facts[:, 0], facts[:, 1])
+    member = facts[:, 0] if head else facts[:, 2]
+    # group of a fact = its fixed pair (dense ids via unique); the group's member list is the set of distinct members
+    # (the reference's lists keep duplicates of repeated facts, which set the same score to -inf twice: same result)
+    key = a * (int(b.max()) + 1) + b
+    _, inv = torch.unique(key, return_inverse=True)
+    M = int(member.max()) + 1
+    pairs = torch.unique(inv * M + member)                        # sorted: grouped by key, members ascending
+    grp = pairs // M
+    members_sorted = pairs - grp * M
+    sizes = torch.bincount(grp, minlength=int(inv.max()) + 1)
+    start = torch.cumsum(sizes, 0) - sizes
+    cnt = sizes[inv]                                              # list length of every fact = size of its group
+    ptr = torch.zeros(F + 1, dtype=torch.long, device=dev)
+    torch.cumsum(cnt, 0, out=ptr[1:])
+    total = int(ptr[-1])
+    assert total < 2 ** 31, "filter lists exceed int32 indexing; rank the facts in several calls"
+    fact_of = torch.repeat_interleave(torch.arange(F, device=dev), cnt)
+    pos = torch.arange(total, device=dev) - ptr[fact_of] + start[inv[fact_of]]
+    idx = members_sorted[pos]
+    return ptr.to(torch.int32), idx.to(torch.int32).contiguous()
 
 
-RANK_WS_BYTES = 2 << 30      # score workspace per ranking call; larger fact sets are processed in chunks
+RANK_MAX_FACTS = 1 << 20      # facts per ranking call (the C entry point takes 65 535 * 32)
 
 
 def compute_ranks_fast(data, node_embeddings, edge_embeddings, batch_size=16, filtered=True):
     """Ranks of every fact against all N candidate tails, then all candidate heads (loop order of
     link_prediction.py:602).  `batch_size` (the reference's mrr_batchsize chunking of the fact axis, :618-625) does not
-    change any result and is not needed for memory here: facts are processed in chunks sized to a fixed workspace
-    (and to the 65 535-facts-per-call limit of the C entry point).  The filter dictionaries are built over ALL facts of
-    `data`, as the reference does (:597-600).  Returns int64 (2*facts,), 1-based."""
+    change any result and is not needed here: the scores live in registers only (csrc/rank.cu).  The filter lists are
+    built over ALL facts of `data`, as the reference does (:597-600), on the device.  Returns int64 (2*facts,), 1-based."""
     E = node_embeddings.detach().float().contiguous()
     nv.require_cuda(E, "node_embeddings")
     dev = E.device
     Rel = edge_embeddings.detach().to(dev).float().contiguous()
-    data_h = torch.as_tensor(data).cpu().long()
-    facts = data_h.to(dev).contiguous()
+    facts = torch.as_tensor(data).to(dev).long().contiguous()
     F, N, h = facts.shape[0], E.shape[0], E.shape[1]
-    data_np = data_h.numpy()
-    true_heads, true_tails = truedicts(data_np) if filtered else (None, None)
     out = torch.empty(2 * F, dtype=torch.int64, device=dev)
-    chunk = int(max(1, min(65535, RANK_WS_BYTES // (4 * N), F)))
-    ws = torch.empty(max(chunk * N, 1), dtype=torch.float32, device=dev)
     for k, head in enumerate((False, True)):
-        for f0 in range(0, F, chunk):
-            f1 = min(F, f0 + chunk)
-            fptr = fidx = None
+        fptr = fidx = None
+        if filtered:
+            fptr, fidx = filter_csr_device(facts, head)
+        for f0 in range(0, F, RANK_MAX_FACTS):
+            f1 = min(F, f0 + RANK_MAX_FACTS)
+            ws = torch.empty(int(nv.lib().mrgcn_distmult_rank_ws_elems(f1 - f0)), dtype=torch.int32, device=dev)
+            fp = None
             if filtered:
-                p_, i_ = _filter_csr(data_np[f0:f1], true_heads if head else true_tails, head)
-                fptr, fidx = torch.from_numpy(p_).to(dev), torch.from_numpy(i_).to(dev)
+                fp = (fptr[f0:f1 + 1] - fptr[f0]).contiguous()
+                fi = fidx[int(fptr[f0]):] if f0 else fidx
             with torch.cuda.device(dev):
                 nv.check(nv.lib().mrgcn_distmult_rank(nv.ptr(facts[f0:f1]), f1 - f0, int(head), nv.ptr(E), nv.ptr(Rel), N, h,
-                                                      nv.ptr(fptr), nv.ptr(fidx), nv.ptr(ws), nv.ptr(out[k * F + f0:]),
-                                                      nv.stream_ptr()), "distmult_rank")
+                                                      nv.ptr(fp), nv.ptr(fi) if filtered else None, nv.ptr(ws),
+                                                      nv.ptr(out[k * F + f0:]), nv.stream_ptr()), "distmult_rank")
     return out

@@ -147,3 +147,42 @@ def test_tab_plan_invariants_and_reduction_semantics():
     # an empty graph gives an empty plan
     z = build_tab_plan(torch.zeros(5, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), 0, 4, R, thresh)
     assert z["n_tasks"] == 0 and z["n_tiles"] == 0 and z["n_pieces"] == 0 and z["n_wsrc"] == 4
+
+
+def test_device_worklists_match_the_numpy_ones():
+    """chunk_worklist_device / hub_segments_device (torch ops, used at graph build) against the NumPy definitions."""
+    import torch
+    from mrgcn_b200.graph import chunk_worklist, chunk_worklist_device, hub_segments, hub_segments_device
+    rng = np.random.default_rng(3)
+    R = 7
+    cnt = rng.integers(0, 900, size=3 * R)
+    grp = np.concatenate([[0], np.cumsum(cnt)])
+    want = chunk_worklist(grp, R, 128)
+    got = chunk_worklist_device(torch.from_numpy(grp), R, 128)
+    for a, b in zip(want, got):
+        assert np.array_equal(np.asarray(a), b.numpy())
+    deg = rng.integers(129, 5000, size=17)
+    hub, first = hub_segments(deg, 512)
+    hub2, first2 = hub_segments_device(torch.from_numpy(deg), 512)
+    assert np.array_equal(hub, hub2.numpy()) and np.array_equal(first, first2.numpy())
+
+
+def test_filter_csr_matches_reference_dictionaries():
+    """filter_csr_device == the reference's truedicts lists (link_prediction.py:575-591), as sets, for both sides,
+    including repeated facts."""
+    import torch
+    from mrgcn_b200.tasks.link_prediction import filter_csr_device
+    from oracle import reference_port as rp
+    rng = np.random.default_rng(0)
+    data = np.stack([rng.integers(0, 30, 200), rng.integers(0, 4, 200), rng.integers(0, 30, 200)], 1)
+    data[50:60] = data[40:50]
+    heads, tails = rp.true_dicts(torch.from_numpy(data))
+    facts = torch.from_numpy(data).long()
+    for head in (False, True):
+        ptr, idx = filter_csr_device(facts, head)
+        assert ptr.dtype == torch.int32 and idx.dtype == torch.int32
+        for f, (s, p, o) in enumerate(data.tolist()):
+            want = sorted(set(heads[(p, o)] if head else tails[(s, p)]))
+            assert idx[ptr[f]:ptr[f + 1]].tolist() == want
+    ptr, idx = filter_csr_device(facts[:0], True)
+    assert ptr.tolist() == [0]
