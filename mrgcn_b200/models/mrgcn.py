@@ -139,8 +139,29 @@ class MRGCN(nn.Module):
         self.devices["relational"] = device
         self.rgcn.to(device)
         self.X_device = device if all(d.type == device.type for d in self.devices.values()) else torch.device("cpu")
+        from ..upload import FeaturePrefetcher
+        self._prefetcher = FeaturePrefetcher()
 
     # ------------------------------------------------------------------------------------------
+    def prefetch(self, batch):
+        """Start the host -> device copy of batch.X[0] for a LATER forward(batch) on a copy stream (mrgcn_b200/upload.py), so
+        that it overlaps the step that is computing now.  Optional: without it forward uploads in line, as the reference does
+        (mrgcn.py:199-204).  Only the encoder-free feature path is prefetched (with modality encoders the matrix is assembled
+        on the device anyway).  Returns True when a copy was started."""
+        if self.compute_modality_embeddings or self.rgcn.layers["layer_0"].featureless:
+            return False
+        X = self._own_rows(torch.as_tensor(batch.X[0]))
+        if X.device.type != "cpu":
+            return False
+        return self._prefetcher.start(X, self.devices["relational"])
+
+    def _own_rows(self, X):
+        """The rows of the host matrix this process uploads: all of them, or the rank's range when layer 0 is
+        source-partitioned."""
+        if self.partitioned and self.rgcn.layer0_is_source_partitioned():
+            return X[self.rgcn.lay.lo:self.rgcn.lay.hi]
+        return X
+
     def forward(self, batch):
         if isinstance(batch, MiniBatch) or type(batch).__name__ == "MiniBatch":
             return self._forward(batch, batch.A.neighbours[-1])
@@ -177,17 +198,20 @@ class MRGCN(nn.Module):
             self._part_A = A
         if rg.layers["layer_0"].featureless:
             return rg.forward_all(None)
-        X = torch.as_tensor(X)
-        if rg.layer0_is_source_partitioned():
-            X_in = X[lay.lo:lay.hi].to(dev, non_blocking=True).float()          # own rows only
-        else:
-            X_in = lay.to_padded(X.to(dev, non_blocking=True).float())
+        X_in = self._upload_features(self._own_rows(torch.as_tensor(X)), dev).float()          # own rows only, or all
+        if not rg.layer0_is_source_partitioned():
+            X_in = lay.to_padded(X_in)
         return rg.forward_all(X_in)
 
     def _upload_features(self, X, dev):
         """Host feature matrix -> device, every call (as mrgcn.py:203-204 does).  One contiguous DMA (a pitched 2-D copy of
         604-byte rows was measured at 5 GB/s, the contiguous one runs at the PCIe rate); the layer pads the rows on the
-        device for the projection kernel's tensor-map loads (csrc/feat_proj.cu: k_pad_rows)."""
+        device for the projection kernel's tensor-map loads (csrc/feat_proj.cu: k_pad_rows).  A copy started earlier by
+        prefetch() is used instead when there is one."""
+        if X.device.type == "cpu":
+            ahead = self._prefetcher.take(X, dev)
+            if ahead is not None:
+                return ahead
         return X.to(dev, non_blocking=True)
 
     def _compute_modality_embeddings(self, F, batch_idx):

@@ -554,3 +554,43 @@ def test_device_frontier_expansion_matches_host_batches(golden):
     Xo = torch.from_numpy(g["X"]).to(DEV)[devb.neighbours[1]]
     out = model(Xo, devb)
     check(out, g["out"], None, "minibatch through DeviceABatch")
+
+
+def test_prefetched_upload_matches_inline_upload():
+    """MRGCN.prefetch (copy-stream upload into rotating resident buffers) must hand every forward the matrix that was current
+    for it: two different host matrices alternate over several steps, with backward in between, and every output and
+    weight gradient must be bit-identical to the in-line upload's."""
+    import torch.nn as nn
+    from mrgcn_b200.data.batch import FullBatch
+    from mrgcn_b200.graph import RelGraph
+    from mrgcn_b200.models.mrgcn import MRGCN
+    from mrgcn_b200.synth import synth_triples
+    N, P, ind = 5000, 3, 40
+    g = RelGraph.from_triples(synth_triples(N, P, 60000, seed=3), N, P, device=DEV)
+    R = g.R
+    torch.manual_seed(0)
+    model = MRGCN([(ind, 10, "mrgcn", nn.ReLU()), (10, 5, "mrgcn", None)], [], R, N, num_bases=8, p_dropout=0.0,
+                  featureless=False, bias=False, link_prediction=False)
+    Xs = [torch.randn(N, ind).pin_memory() for _ in range(2)]
+    batches = [FullBatch(g, [x], np.arange(N)) for x in Xs]
+    G = torch.randn(N, 5, device=DEV)
+
+    def run(prefetch):
+        outs = []
+        if prefetch:
+            assert model.prefetch(batches[0])
+        for i in range(6):
+            for p in model.parameters():
+                p.grad = None
+            if prefetch and i + 1 < 6:
+                assert model.prefetch(batches[(i + 1) % 2])
+            out = model(batches[i % 2])
+            (out * G).sum().backward()
+            outs.append((out.detach().clone(), model.rgcn.layers["layer_0"].weight_F.grad.clone()))
+        torch.cuda.synchronize()
+        return outs
+    a, b = run(False), run(True)
+    assert model._prefetcher.copies == 6 and len(model._prefetcher.slots) <= 3
+    for (o1, g1), (o2, g2) in zip(a, b):
+        assert torch.equal(o1, o2) and torch.equal(g1, g2)
+    assert not torch.equal(a[0][0], a[1][0])
