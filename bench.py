@@ -419,10 +419,14 @@ def main():
                 return bce(score_distmult_bc((trip_d[:, 0], trip_d[:, 1], trip_d[:, 2]), out, rg.relations), Y_d) / n_lab
             return ce(out[idx_d], y_d) / n_lab
 
+        def step_loss():
+            return loss_of(rg(Xd, graph))
+        step_after = None
+
         def step_device():
             for p in params:
                 p.grad = None
-            loss = loss_of(rg(Xd, graph))
+            loss = step_loss()
             loss.backward()
             return loss
 
@@ -463,16 +467,19 @@ def main():
             idx_d, y_d = torch.from_numpy(lab_idx[m] - lo).to(dev), torch.from_numpy(lab_y[m]).to(dev)
             idx_all, y_all = torch.from_numpy(lab_idx).to(dev), torch.from_numpy(lab_y).to(dev)
 
-        def step_device():
+        def step_loss():
             rg.hooks_enabled = False
-            for p in params:
-                p.grad = None
             H = rg(Xd)                                                       # the rank's rows
             if is_lp:      # all-gather E once, score the rank's shard of the triples, reduce-scatter dE in backward
                 E_all = part.GatherRows.apply(H, lay)
-                loss = bce(score_distmult_bc((trip_d[:, 0], trip_d[:, 1], trip_d[:, 2]), E_all, rg.relations), Y_d) / n_lab
-            else:
-                loss = ce(H[idx_d], y_d) / n_lab
+                return bce(score_distmult_bc((trip_d[:, 0], trip_d[:, 1], trip_d[:, 2]), E_all, rg.relations), Y_d) / n_lab
+            return ce(H[idx_d], y_d) / n_lab
+        step_after = rg.sync_grads
+
+        def step_device():
+            for p in params:
+                p.grad = None
+            loss = step_loss()
             loss.backward()
             rg.sync_grads()
             return loss
@@ -599,17 +606,8 @@ def main():
     run_step, graphed = step_device, False
     if not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step_device()
-            torch.cuda.current_stream().wait_stream(side)
-            barrier()
-            cg = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cg):
-                step_device()
-            run_step, graphed = cg.replay, True
+            from mrgcn_b200.stepping import GraphedStep      # the product API: capture once, replay per epoch
+            run_step, graphed = GraphedStep(step_loss, params, after_backward=step_after, barrier=barrier), True
         except Exception as exc:     # pragma: no cover
             if rank == 0:
                 print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)

@@ -594,3 +594,33 @@ def test_prefetched_upload_matches_inline_upload():
     for (o1, g1), (o2, g2) in zip(a, b):
         assert torch.equal(o1, o2) and torch.equal(g1, g2)
     assert not torch.equal(a[0][0], a[1][0])
+
+
+def test_graphed_step_replays_the_eager_step():
+    """GraphedStep (mrgcn_b200/stepping.py): the captured step's loss and gradients equal the eager step's bit for bit,
+    and follow in-place updates of the weights between replays."""
+    import torch.nn as nn
+    from mrgcn_b200.graph import RelGraph
+    from mrgcn_b200.models.rgcn import RGCN
+    from mrgcn_b200.stepping import GraphedStep
+    from mrgcn_b200.synth import synth_triples
+    N, P, ind = 4000, 3, 40
+    g = RelGraph.from_triples(synth_triples(N, P, 50000, seed=5), N, P, device=DEV)
+    torch.manual_seed(0)
+    model = RGCN([(ind, 10, "mrgcn", nn.ReLU()), (10, 5, "mrgcn", None)], g.R, N, 8, 0.0, False, False, False).to(DEV)
+    X = torch.randn(N, ind, device=DEV)
+    y = torch.randint(0, 5, (N,), device=DEV)
+    ce = nn.CrossEntropyLoss()
+    params = list(model.parameters())
+    step = GraphedStep(lambda: ce(model(X, g), y), params)
+    for it in range(3):
+        loss_g = step().clone()
+        grads_g = [p.grad.clone() for p in params]
+        loss_e = step.eager()
+        for a, p in zip(grads_g, params):
+            assert torch.equal(a, p.grad)
+        assert torch.equal(loss_g, loss_e)
+        with torch.no_grad():
+            for p in params:
+                p.add_(0.01 * torch.randn_like(p))
+    assert step.graph is not None
