@@ -169,6 +169,10 @@ def algorithmic_bytes(g, in0, dims, B, fused):
         add("tab_msg_fwd", Bn * NS * h * 4 * (2 if fused else 1) + E * 8 + ntask * 8 + NS * 4 + E * h * 4 + R * Bn * 4 * (2 if fused else 1))
         add("tab_bwd_w", E * (12 + h * 4) + NS * 8 + Bn * NS * h * 4 + R * Bn * 4)
         add("tab_bwd_c", Bn * NS * h * 4 + E * (8 + h * 4) + ntask * 8 + E * 4 + npc * (4 + Bn * 4))
+        # the tile-staging pair (default for narrow outputs): same algorithmic work; ident_bwd_c's E x B scratch (`cbuf`) and
+        # its reduction are implementation traffic, not algorithmic bytes, so they lower its achieved figure
+        add("ident_bwd_w", E * (12 + h * 4) + NS * 8 + Bn * NS * h * 4 + R * Bn * 4)
+        add("ident_bwd_c", Bn * NS * h * 4 + E * (12 + h * 4) + NS * 4 + R * Bn * 4)
         add("comp_block_reduce", npc * (4 + Bn * 4) + nblk * Bn * 4)
         add("comp_reduce", nblk * Bn * 4 + R * Bn * 4)
     if in0 and not fused:
