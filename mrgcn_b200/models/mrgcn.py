@@ -155,6 +155,12 @@ class MRGCN(nn.Module):
             return False
         return self._prefetcher.start(X, self.devices["relational"])
 
+    def upload(self, batch):
+        """The device copy of batch.X[0] (the rank's rows under a node partition): the one prefetch() started, else a copy
+        made now.  For callers that feed a captured step (mrgcn_b200/stepping.py) through a static input buffer:
+        `X_static.copy_(model.upload(batch)); step()`."""
+        return self._upload_features(self._own_rows(torch.as_tensor(batch.X[0])), self.devices["relational"])
+
     def _own_rows(self, X):
         """The rows of the host matrix this process uploads: all of them, or the rank's range when layer 0 is
         source-partitioned."""
