@@ -88,6 +88,10 @@ typedef struct mrgcn_graph {
   int32_t *rel_chunk_ptr; /* [R+1] range in rel_chunk_idx of relation r */
   int32_t *rel_chunk_idx; /* [n_chunks] chunk ids of each relation, in slab order */
   int32_t n_chunks, slab_rows; /* slab_rows: input of mrgcn_graph_build (0 = one slab) */
+  /* optional (NULL = natural order): destination rows / source columns sorted by falling entry count, so that the rows a
+   * warp of the one-pass narrow-layer kernels (narrow.cu) works on have (nearly) equal lengths */
+  int32_t *rows_by_deg; /* [ND] */
+  int32_t *cols_by_deg; /* [NS] */
 } mrgcn_graph;
 
 /* Work plan of the table-term kernels (tab.cu) over the source-major order E2 of one graph; built by the host side

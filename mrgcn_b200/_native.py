@@ -34,6 +34,7 @@ class Graph(C.Structure):
         ("_pad3", C.c_int32),
         ("chunk_rel", C.c_void_p), ("chunk_ptr", C.c_void_p), ("rel_chunk_ptr", C.c_void_p),
         ("rel_chunk_idx", C.c_void_p), ("n_chunks", C.c_int32), ("slab_rows", C.c_int32),
+        ("rows_by_deg", C.c_void_p), ("cols_by_deg", C.c_void_p),
     ]
 
 

@@ -904,14 +904,20 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
         MRGCN_PROF("transpose_w");
         k_transpose_w<<<dim3((unsigned)cdiv(IO, 128), (unsigned)gF->R), 128, 0, st>>>(W, a->wt_ws, in, out);
         MRGCN_LAUNCH_CHECK();
-        if (gF->E > 0)
-          if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, out, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
         AggArgs g{};
         g.ND = (int)NS; g.odim = in; g.ms = msg_stride(in); g.out = a->g_X;
-        g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;
         g.thresh = gF->n_long_cols > 0 ? gF->long_col_thresh : 0;
         HubSegs hs{gF->long_cols, gF->col_seg_hub, gF->col_seg_first, gF->n_long_cols, gF->n_col_segs, gF->long_seg, f.hub_ws};
-        if (int rc = launch_agg(g, hs, st, "feat_bwd_x_agg")) return rc;
+        if (narrow_supported(gF->R, out, in)) {
+          // dX[j, :] = sum_{e: src = j} val_e * W[rel_e] . gact[dst_e, :] in one pass over the source-major order (narrow.cu)
+          NarrowArgs n{gF->cols_by_deg, gF->colptr, gF->e2_dst, gF->e2_rel, gF->e2_val, a->gact, a->wt_ws, out, gF->R, out, in, g};
+          if (int rc = launch_narrow(n, hs, st, "narrow_bwd_x")) return rc;
+        } else {
+          if (gF->E > 0)
+            if (int rc = launch_feat_msg(gF, gF->e3_dst, a->gact, out, a->wt_ws, a->msgx_ws, out, in, st, "feat_bwd_x_msg")) return rc;
+          g.msgF = a->msgx_ws; g.pF = gF->e2_to_e3; g.rowptrF = gF->colptr;
+          if (int rc = launch_agg(g, hs, st, "feat_bwd_x_agg")) return rc;
+        }
       }
     }
   }

@@ -331,13 +331,6 @@ __device__ __forceinline__ int row_degree(const AggArgs &a, int i) {
   return d;
 }
 
-__device__ __forceinline__ void agg_store(const AggArgs &a, int i, int o, float acc) {
-  if (a.addend) acc += a.addend[(size_t)i * a.odim + o];
-  if (a.bias) acc += a.bias[o];
-  if (a.mask) acc *= a.mask[i];
-  if (a.relu) acc = fmaxf(acc, 0.f);
-  a.out[(size_t)i * a.odim + o] = acc;
-}
 
 // short rows: one sub-warp group of `odim` lanes per row (32/odim rows per warp), or a whole warp per row
 __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
@@ -680,6 +673,13 @@ extern "C" int mrgcn_rgcn_layer_fwd(const mrgcn_layer_args *a, mrgcn_stream_t st
       MRGCN_REQUIRE(a->comp_F && a->wmix, MRGCN_E_BADARG, "layer_fwd: comp_F/wmix missing");
       if (int rc = launch_basis_mix_fwd(a->comp_F, a->weight_F, a->wmix, gF->R, B, in * out, st)) return rc;
       W = a->wmix;
+    }
+    if (!hasI && narrow_supported(gF->R, in, out)) {
+      // feature-only narrow layer: gather, transform and aggregate in one pass (narrow.cu), no message buffer
+      NarrowArgs n{gF->rows_by_deg, gF->rowptr, gF->e1_src, gF->e1_rel, gF->e1_val, a->X, W, ldx, gF->R, in, out, g};
+      n.epi.thresh = gF->n_long_rows > 0 ? gF->long_row_thresh : 0;
+      HubSegs hs{gF->long_rows, gF->row_seg_hub, gF->row_seg_first, gF->n_long_rows, gF->n_row_segs, gF->long_seg, a->hub_ws};
+      return launch_narrow(n, hs, st, "narrow_fwd");
     }
     if (!fused_feat) {
       MRGCN_REQUIRE(a->msg_F, MRGCN_E_BADARG, "layer_fwd: msg_F missing");

@@ -44,6 +44,15 @@ struct AggArgs {
   int ND, odim, relu, thresh;
 };
 
+// epilogue of every aggregation: + addend, + bias, node-dropout mask, ReLU (models/rgcn.py:78-87, layers/graph.py:99-102)
+__device__ __forceinline__ void agg_store(const AggArgs &a, int i, int o, float acc) {
+  if (a.addend) acc += a.addend[(size_t)i * a.odim + o];
+  if (a.bias) acc += a.bias[o];
+  if (a.mask) acc *= a.mask[i];
+  if (a.relu) acc = fmaxf(acc, 0.f);
+  a.out[(size_t)i * a.odim + o] = acc;
+}
+
 int launch_basis_mix_fwd(const float *comp, const float *V, float *W, int R, int B, int IO, cudaStream_t st);
 // msg[e3,:] = val_e * Xrows[gather[e3], :] . W[r]   (gather = e3_src forward, e3_dst for the input gradient)
 int launch_feat_msg(const mrgcn_graph *g, const int32_t *gather, const float *X, int ldx, const float *W, float *msg, int in,
@@ -56,6 +65,19 @@ struct HubSegs {
   float *ws;
 };
 int launch_agg(const AggArgs &a, const HubSegs &h, cudaStream_t st, const char *prof_name);
+// narrow layers (narrow.cu): gather, transform and aggregate in one pass, W resident in shared memory, no message buffer:
+//   out[i, :] = epilogue( sum_{e in row i} val_e * X[nbr_e, :] . W[rel_e] )      W: [R][in][out]
+// rows/nbr/rel/val are a row-major edge order (E1 for the forward pass, E2 with W^T for the input gradient); `epi` carries
+// ND, odim (= out), thresh and the epilogue.  Hub rows go through `h` (one CTA per segment, partials combined in order).
+struct NarrowArgs {
+  const int32_t *order;   // rows in processing order (by falling length) or NULL
+  const int32_t *rowptr, *nbr, *rel;
+  const float *val, *X, *W;
+  int ldx, R, in, out;
+  AggArgs epi;
+};
+bool narrow_supported(int R, int in, int out);
+int launch_narrow(const NarrowArgs &a, const HubSegs &h, cudaStream_t st, const char *prof_name);
 // per-basis projection of the node features on the tensor cores (feat_proj.cu): P[j, b*out + o] = X[j, :] . V[b, :, o]
 bool feat_proj_supported(int in, int ldx, int B, int out);
 int launch_feat_proj(const float *X, int64_t N, int in, int ldx, const float *V, int B, int out, float *vt_ws, float *xpad_ws,

@@ -239,6 +239,11 @@ class RelGraph:
         c.chunk_rel, c.chunk_ptr = self.chunk_rel.data_ptr(), self.chunk_ptr.data_ptr()
         c.rel_chunk_ptr, c.n_chunks = self.rel_chunk_ptr.data_ptr(), n_chunks
         c.rel_chunk_idx = self.rel_chunk_idx.data_ptr()
+        # rows / columns by falling length: the warps of the one-pass narrow-layer kernels (csrc/narrow.cu) then hold rows
+        # of (nearly) equal length instead of waiting for the longest of eight
+        self.rows_by_deg = torch.argsort(deg_r, descending=True, stable=True).to(_I32) if self.ND else one
+        self.cols_by_deg = torch.argsort(deg_c, descending=True, stable=True).to(_I32) if self.NS else one
+        c.rows_by_deg, c.cols_by_deg = self.rows_by_deg.data_ptr(), self.cols_by_deg.data_ptr()
 
     # ------------------------------------------------------------------------------------------
     @classmethod
