@@ -128,6 +128,10 @@ int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out);
  * MRGCN_TAB=<mask> in the environment forces it at start-up. */
 void mrgcn_set_tab_mask(int32_t mask);
 
+/* 1 when a feature-only layer of this shape runs in one pass (csrc/narrow.cu: R x in x out weights resident in shared
+ * memory, no per-edge message buffer: msg_F / msgx_ws may then be NULL / a dummy); MRGCN_NARROW=0 disables it. */
+int32_t mrgcn_narrow_supported(int32_t R, int32_t in_dim, int32_t out_dim);
+
 /* Re-emit the reference's stacked adjacency as E1/E2/E3.
  * Replaces: scipy CSR -> torch COO hand-off (mrgcn/data/utils.py:165-170, mrgcn/data/batch.py:144-149)
  * and the per-call coalesce/sort inside torch.mm(sparse, dense) (mrgcn/layers/graph.py:75,95).

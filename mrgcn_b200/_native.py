@@ -113,6 +113,7 @@ SYMBOLS = {
     "mrgcn_distmult_bwd_ws_elems": (C.c_int64, [C.c_int64]),
     "mrgcn_distmult_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrgcn_narrow_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgcn_distmult_rank_ws_elems": (C.c_int64, [C.c_int64]),
     "mrgcn_distmult_rank": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,6 +1,5 @@
-// DistMult scorer, its backward and the ranking pass
-// (replaces /root/reference/mrgcn/tasks/link_prediction.py:645-665 score_distmult_bc,
-//  :557-573 filter_scores_ and :593-643 compute_ranks_fast).
+// DistMult scorer and its backward
+// (replaces /root/reference/mrgcn/tasks/link_prediction.py:645-665 score_distmult_bc; the ranking pass is rank.cu).
 // Fused gather-multiply-reduce: nothing of shape (n, h) or (b, N, h) is materialised.
 #include <cub/device/device_radix_sort.cuh>
 

@@ -255,3 +255,7 @@ int launch_narrow(const NarrowArgs &a, const HubSegs &h, cudaStream_t st, const 
 }
 
 }  // namespace mrgcn
+
+extern "C" int32_t mrgcn_narrow_supported(int32_t R, int32_t in_dim, int32_t out_dim) {
+  return mrgcn::narrow_supported(R, in_dim, out_dim) ? 1 : 0;
+}

@@ -103,7 +103,9 @@ class _LayerFn(torch.autograd.Function):
                 if x_stride != pitch:
                     xpad_ws = _empty(gI.NS * pitch, dev)
         msg_I = _empty(gI.E * ms, dev) if (hasI and B) else None
-        msg_F = _empty(gF.E * ms, dev) if (hasF and proj is None) else None
+        # feature-only narrow layers run in one pass (csrc/narrow.cu): no per-edge messages either
+        narrow_f = hasF and not hasI and bool(nv.lib().mrgcn_narrow_supported(gF.R, in_dim, out_dim))
+        msg_F = _empty(gF.E * ms, dev) if (hasF and proj is None and not narrow_f) else None
         a = nv.LayerArgs()
         a.gI = C.pointer(gI.c) if hasI else None
         a.gF = C.pointer(gF.c) if hasF else None
@@ -167,7 +169,10 @@ class _LayerFn(torch.autograd.Function):
         if hasF and need[0]:
             g_X = torch.empty(X.shape, dtype=torch.float32, device=dev)
             wt_ws = _empty(gF.R * in_dim * out_dim, dev)
-            msgx_ws = _empty(gF.E * int(nv.lib().mrgcn_msg_stride(in_dim)), dev)
+            if nv.lib().mrgcn_narrow_supported(gF.R, out_dim, in_dim):
+                msgx_ws = _empty(4, dev)          # the input gradient runs in one pass: no per-edge messages
+            else:
+                msgx_ws = _empty(gF.E * int(nv.lib().mrgcn_msg_stride(in_dim)), dev)
         colsum = None
         if bias is not None and need[5]:
             g_b = torch.empty_like(bias)
