@@ -173,6 +173,9 @@ def algorithmic_bytes(g, in0, dims, B, fused):
         # its reduction are implementation traffic, not algorithmic bytes, so they lower its achieved figure
         add("ident_bwd_w", E * (12 + h * 4) + NS * 8 + Bn * NS * h * 4 + R * Bn * 4)
         add("ident_bwd_c", Bn * NS * h * 4 + E * (12 + h * 4) + NS * 4 + R * Bn * 4)
+        # one pass for both (ident_bwd.cu): table read once, gradient written once, edges and gact rows once; its scratch rows
+        # (E x B, written in E3 order and streamed by comp_chunk_reduce) are again implementation traffic
+        add("ident_bwd_fused", 2 * Bn * NS * h * 4 + E * (16 + h * 4) + NS * 4 + R * Bn * 4)
         add("comp_block_reduce", npc * (4 + Bn * 4) + nblk * Bn * 4)
         add("comp_reduce", nblk * Bn * 4 + R * Bn * 4)
     if in0 and not fused:

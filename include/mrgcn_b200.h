@@ -128,6 +128,11 @@ int32_t mrgcn_tab_mode(int32_t BI, int32_t BF, int32_t out);
  * MRGCN_TAB=<mask> in the environment forces it at start-up. */
 void mrgcn_set_tab_mask(int32_t mask);
 
+/* Identity-term backward (B > 0): 1 (default) = one pass for g_weight_I and the comp-gradient scratch rows
+ * (csrc/ident_bwd.cu: even out <= 16, B <= 64), 0 = the separate round-1 kernels.  MRGCN_IDENT_FUSED=0 in the environment
+ * does the same at start-up. */
+void mrgcn_set_ident_fused(int32_t on);
+
 /* 1 when a feature-only layer of this shape runs in one pass (csrc/narrow.cu: R x in x out weights resident in shared
  * memory, no per-edge message buffer: msg_F / msgx_ws may then be NULL / a dummy); MRGCN_NARROW=0 disables it. */
 int32_t mrgcn_narrow_supported(int32_t R, int32_t in_dim, int32_t out_dim);

@@ -94,6 +94,7 @@ SYMBOLS = {
     "mrgcn_msg_stride": (C.c_int32, [C.c_int32]),
     "mrgcn_tab_mode": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgcn_set_tab_mask": (None, [C.c_int32]),
+    "mrgcn_set_ident_fused": (None, [C.c_int32]),
     "mrgcn_feat_proj_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgcn_feat_proj": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),

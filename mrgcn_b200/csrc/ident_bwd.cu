@@ -1,0 +1,404 @@
+// Identity-term backward with basis decomposition in ONE pass over the source-major edge order E2
+// (autograd through /root/reference/mrgcn/layers/graph.py:69-75):
+//
+//   t_e                = val_e * gact[dst_e, :]
+//   g_weight_I[b,j,:]  = sum_{e: src = j} comp_I[rel_e, b] * t_e                    (written once, 4*B*NS*out bytes)
+//   cbuf[e3(e), b]     = <weight_I[b, j, :], t_e>     ->  g_comp_I[r, b] = fixed-order sum over the E3 range of r
+//
+// Round 1 did this in three kernels (ident_bwd_w, ident_bwd_c, comp_chunk_reduce) that read the edges, gact and the
+// scratch rows several times.  Here a lane owns one basis b (two when B > 32): the rows weight_I[b, j, :] and the
+// accumulators g_weight_I[b, j, :] of the warp's current source live in registers, so per edge the warp reads only the
+// edge's t_e (broadcast) and comp_I[rel_e, :] (one coalesced row) from shared memory.  The scratch rows are written at
+// the edge's position in the relation-major order E3, so that the per-relation reduction streams them contiguously.
+//
+// One persistent CTA per SM, four roles joined by mbarriers (no CTA-wide barrier after start-up):
+//   loader warp     cp.async.bulk (TMA engine): per tile of TJ sources the B runs weight_I[b, j0 : j0+TJ, :] and the
+//                   tile's slices of e2_dst / e2_rel / e2_val / e2_to_e3 into a ring of S stages
+//   storer warp     when the compute warps are done with a stage it holds g_weight_I of the tile IN PLACE of weight_I
+//                   and goes back to HBM with cp.async.bulk shared -> global (B runs of TJ*out floats: full-line stores)
+//   gather warps    t_e of every staged edge (all gathers of a tile in flight at once) into the stage
+//   compute warps   sources of the tile, handed out by a counter in the stage header
+// Hub sources (more than `thresh` edges) keep their g_weight_I in k_ident_bwd_w_long (launched afterwards: it overwrites
+// the rows this kernel leaves untouched); their scratch rows are produced here, chunk by chunk across the compute warps.
+// Every sum is taken in edge order by one thread: bit-reproducible, no atomics on floats.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+#include "ident_pipe.cuh"
+#include "rgcn_internal.cuh"
+
+namespace mrgcn {
+namespace {
+
+constexpr int kCW = 12;  // compute warps
+constexpr int kGW = 4;   // gather warps
+constexpr int kFusedThreads = (kCW + kGW + 2) * 32;   // + loader + storer
+constexpr int kHdrInts = 64;   // stage header: 0 e_lo, 1 e_hi, 2 j0, 3 a_lo, 4 source counter, 5 hub bits, 16.. colptr[j0 .. j0+TJ]
+
+struct FusedCfg {
+  int NS, R, B, out, TJ, S, ntiles, mcap, thresh;
+  int vstride;       // floats between the runs of consecutive bases inside a stage (TJ*out, padded against bank conflicts)
+  int off_v, off_meta, off_ts, stage_bytes;   // byte offsets inside a stage
+  int comp_bytes;
+};
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// one edge: the warp's lanes hold v (rows of weight_I) and g (accumulators) of NB bases each
+template <int OUT, int NB>
+__device__ __forceinline__ void edge_body(const float2 (&t)[OUT / 2], const float (&c)[NB], const float2 (&v)[NB][OUT / 2],
+                                          float2 (&g)[NB][OUT / 2], float (&d)[NB], bool do_g) {
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < OUT / 2; ++q) fma2v(a2, v[nb][q], t[q]);
+    d[nb] = a2.x + a2.y;
+    if (do_g) {
+#pragma unroll
+      for (int q = 0; q < OUT / 2; ++q) fma2(g[nb][q], c[nb], t[q]);
+    }
+  }
+}
+
+template <int OUT, int NB>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
+                  const int32_t *__restrict__ e2_dst, const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
+                  const int32_t *__restrict__ e2_to_e3, const float *__restrict__ gact, float *__restrict__ gW,
+                  float *__restrict__ cbuf, FusedCfg p) {
+  constexpr int TP = (OUT + 3) & ~3;   // floats per staged t_e row
+  constexpr int Q = OUT / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *tready = full + p.S;
+  uint64_t *done = tready + p.S;
+  uint64_t *freeb = done + p.S;
+  float *comp_s = reinterpret_cast<float *>(smem_raw + 256);
+  unsigned char *stages = smem_raw + 256 + p.comp_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = p.B, S = p.S, TJ = p.TJ;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&tready[s], kGW); mbar_init(&done[s], kCW); mbar_init(&freeb[s], 1); }
+    mbar_fence_init();
+  }
+  for (int x = threadIdx.x; x < p.R * B; x += kFusedThreads) comp_s[x] = __ldg(comp + x);
+  __syncthreads();
+  const int ntiles_mine = (int)blockIdx.x < p.ntiles ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == kCW + kGW) {
+    // ============================== loader: weight_I runs + edge metadata of tile k into stage k % S ==============================
+    const uint32_t run_bytes = (uint32_t)TJ * OUT * 4;
+    auto tile_j0 = [&](int k) {
+      int j0 = ((int)blockIdx.x + k * (int)gridDim.x) * TJ;
+      return j0 + TJ > p.NS ? p.NS - TJ : j0;   // the last tile overlaps its neighbour: the same values are written twice
+    };
+    int cpv = 0;   // colptr[j0 + lane] of the next tile: loaded one tile ahead, off the critical path
+    if (ntiles_mine > 0 && lane <= TJ) cpv = colptr[tile_j0(0) + lane];
+    for (int k = 0; k < ntiles_mine; ++k) {
+      const int s = k % S;
+      unsigned char *st = stages + (size_t)s * p.stage_bytes;
+      int *hdr = reinterpret_cast<int *>(st);
+      float *vs = reinterpret_cast<float *>(st + p.off_v);
+      const int j0 = tile_j0(k);
+      const int cur = cpv;
+      if (k + 1 < ntiles_mine && lane <= TJ) cpv = colptr[tile_j0(k + 1) + lane];
+      if (k >= S) mbar_wait(&freeb[s], ((k / S) - 1) & 1, 7);   // the stage's previous tile has left for HBM
+      const int e_lo = __shfl_sync(0xffffffffu, cur, 0), e_hi = __shfl_sync(0xffffffffu, cur, TJ);
+      const int nxt = __shfl_down_sync(0xffffffffu, cur, 1);
+      const unsigned hubs = __ballot_sync(0xffffffffu, lane < TJ && p.thresh > 0 && nxt - cur > p.thresh);
+      if (lane <= TJ) hdr[16 + lane] = cur;
+      const int a_lo = e_lo & ~3;
+      int cnt = min(e_hi - a_lo, p.mcap);
+      cnt = e_hi > e_lo ? ((cnt + 3) & ~3) : 0;
+      int *mD = reinterpret_cast<int *>(st + p.off_meta);
+      __syncwarp();
+      if (lane == 0) {
+        hdr[0] = e_lo; hdr[1] = e_hi; hdr[2] = j0; hdr[3] = a_lo; hdr[4] = 0; hdr[5] = (int)hubs;
+        fence_proxy_async();
+        mbar_expect_tx(&full[s], run_bytes * B + 4u * cnt * 4u);
+      }
+      __syncwarp();
+      for (int b = lane; b < B; b += 32)
+        bulk_g2s(vs + (size_t)b * p.vstride, V + ((size_t)b * p.NS + j0) * OUT, run_bytes, &full[s]);
+      if (cnt > 0) {
+        const int ms = p.mcap + 4;
+        if (lane == 28) bulk_g2s(mD, e2_dst + a_lo, cnt * 4u, &full[s]);
+        if (lane == 29) bulk_g2s(mD + ms, e2_rel + a_lo, cnt * 4u, &full[s]);
+        if (lane == 30) bulk_g2s(mD + 2 * ms, e2_val + a_lo, cnt * 4u, &full[s]);
+        if (lane == 31) bulk_g2s(mD + 3 * ms, e2_to_e3 + a_lo, cnt * 4u, &full[s]);
+      }
+    }
+    return;
+  }
+  if (warp == kCW + kGW + 1) {
+    // ============================== storer: a finished stage holds g_weight_I of its tile ==============================
+    const uint32_t run_bytes = (uint32_t)TJ * OUT * 4;
+    for (int k = 0; k < ntiles_mine; ++k) {
+      const int s = k % S;
+      unsigned char *st = stages + (size_t)s * p.stage_bytes;
+      const int *hdr = reinterpret_cast<const int *>(st);
+      const float *vs = reinterpret_cast<const float *>(st + p.off_v);
+      mbar_wait(&done[s], (k / S) & 1, 8);
+      const int j0 = hdr[2];
+      for (int b = lane; b < B; b += 32)
+        bulk_s2g(gW + ((size_t)b * p.NS + j0) * OUT, vs + (size_t)b * p.vstride, run_bytes);
+      bulk_commit();
+      bulk_wait_read0();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&freeb[s]);
+    }
+    bulk_wait0();
+    return;
+  }
+
+  if (warp >= kCW) {
+    // ============================== gather warps: t_e of the staged edges ==============================
+    const int gw = warp - kCW;
+    for (int k = 0; k < ntiles_mine; ++k) {
+      const int s = k % S;
+      mbar_wait(&full[s], (k / S) & 1, 1);
+      unsigned char *st = stages + (size_t)s * p.stage_bytes;
+      const int *hdr = reinterpret_cast<const int *>(st);
+      const int e_lo = hdr[0], e_hi = hdr[1], a_lo = hdr[3];
+      const int ms = p.mcap + 4;
+      const int *mD = reinterpret_cast<const int *>(st + p.off_meta);
+      const float *mV = reinterpret_cast<const float *>(mD + 2 * ms);
+      float *Ts = reinterpret_cast<float *>(st + p.off_ts);
+      const int n_st = min(e_hi - a_lo, p.mcap);
+      for (int idx = (e_lo - a_lo) + gw * 32 + lane; idx < n_st; idx += kGW * 32) {
+        const float val = mV[idx];
+        const float2 *gp = reinterpret_cast<const float2 *>(gact + (size_t)mD[idx] * OUT);
+        float r[TP];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { float2 x = __ldg(gp + q); r[2 * q] = val * x.x; r[2 * q + 1] = val * x.y; }
+#pragma unroll
+        for (int q = OUT; q < TP; ++q) r[q] = 0.f;
+        float4 *dst = reinterpret_cast<float4 *>(Ts + (size_t)idx * TP);
+#pragma unroll
+        for (int q = 0; q < TP / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tready[s]);
+    }
+    return;
+  }
+
+  // ============================== compute warps ==============================
+  const int b0 = lane, b1 = lane + 32;
+  for (int k = 0; k < ntiles_mine; ++k) {
+    const int s = k % S;
+    mbar_wait(&full[s], (k / S) & 1, 2);
+    mbar_wait(&tready[s], (k / S) & 1, 3);
+    unsigned char *st = stages + (size_t)s * p.stage_bytes;
+    int *hdr = reinterpret_cast<int *>(st);
+    const int a_lo = hdr[3];
+    const unsigned hubs = (unsigned)hdr[5];
+    const int *cp = hdr + 16;
+    float *vs = reinterpret_cast<float *>(st + p.off_v);
+    const int ms = p.mcap + 4;
+    const int *mD = reinterpret_cast<const int *>(st + p.off_meta);
+    const int *mR = mD + ms;
+    const int *mP = mD + 3 * ms;
+    const float *Ts = reinterpret_cast<const float *>(st + p.off_ts);
+
+    // v/g of one source: v from the stage, g back into the same place
+    auto load_v = [&](int jl, float2 (&v)[NB][Q]) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int b = lane + 32 * nb;
+        const float2 *vp = reinterpret_cast<const float2 *>(vs + (size_t)b * p.vstride + jl * OUT);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) v[nb][q] = b < B ? vp[q] : make_float2(0.f, 0.f);
+      }
+    };
+    // edges [e0, e0+n) (n <= 32) from global memory: lane i gathers t of edge i, the warp then walks the edges
+    auto chunk_global = [&](int e0, int n, const float2 (&v)[NB][Q], float2 (&g)[NB][Q], bool do_g) {
+      float2 tl[Q];
+      int rel_l = 0, pos_l = 0;
+      if (lane < n) {
+        const int e = e0 + lane;
+        const float val = e2_val[e];
+        rel_l = e2_rel[e]; pos_l = e2_to_e3[e];
+        const float2 *gp = reinterpret_cast<const float2 *>(gact + (size_t)e2_dst[e] * OUT);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { float2 x = __ldg(gp + q); tl[q] = make_float2(val * x.x, val * x.y); }
+      } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) tl[q] = make_float2(0.f, 0.f);
+      }
+      for (int i = 0; i < n; ++i) {
+        float2 t[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { t[q].x = __shfl_sync(0xffffffffu, tl[q].x, i); t[q].y = __shfl_sync(0xffffffffu, tl[q].y, i); }
+        const int rel = __shfl_sync(0xffffffffu, rel_l, i), pos = __shfl_sync(0xffffffffu, pos_l, i);
+        float c[NB], d[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) c[nb] = (lane + 32 * nb < B) ? comp_s[rel * B + lane + 32 * nb] : 0.f;
+        edge_body<OUT, NB>(t, c, v, g, d, do_g);
+        float *crow = cbuf + (size_t)pos * B;
+        if (b0 < B) crow[b0] = d[0];
+        if (NB > 1 && b1 < B) crow[b1] = d[NB - 1];
+      }
+    };
+
+    for (;;) {
+      int jl = 0;
+      if (lane == 0) jl = atomicAdd(&hdr[4], 1);
+      jl = __shfl_sync(0xffffffffu, jl, 0);
+      if (jl >= TJ) break;
+      if ((hubs >> jl) & 1u) continue;   // hub: see below
+      const int s_lo = cp[jl], s_hi = cp[jl + 1];
+      float2 v[NB][Q], g[NB][Q];
+      load_v(jl, v);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[nb][q] = make_float2(0.f, 0.f);
+      if (s_hi - a_lo <= p.mcap) {
+        // every edge of the source is staged
+        // (the metadata arrays have 4 words of slack: the look-ahead of the last edge stays inside them)
+        const int *rp = mR + (s_lo - a_lo), *pp = mP + (s_lo - a_lo);
+        const float *tptr = Ts + (size_t)(s_lo - a_lo) * TP;
+        const float *cl = comp_s + lane;
+        float *cb = cbuf + lane;
+        int rel = rp[0], pos = pp[0];
+        for (int n = s_hi - s_lo; n > 0; --n) {
+          ++rp; ++pp;
+          const int rel_n = rp[0], pos_n = pp[0];
+          float2 t[Q];
+          const float4 *tp = reinterpret_cast<const float4 *>(tptr);
+#pragma unroll
+          for (int q = 0; q < Q / 2; ++q) { float4 x = tp[q]; t[2 * q] = make_float2(x.x, x.y); t[2 * q + 1] = make_float2(x.z, x.w); }
+          if constexpr (OUT % 4 != 0) t[Q - 1] = *reinterpret_cast<const float2 *>(tptr + OUT - 2);
+          tptr += TP;
+          float c[NB], d[NB];
+          const float *cr = cl + rel * B;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) c[nb] = (lane + 32 * nb < B) ? cr[32 * nb] : 0.f;
+          edge_body<OUT, NB>(t, c, v, g, d, true);
+          float *crow = cb + (size_t)pos * B;
+          if (b0 < B) crow[0] = d[0];
+          if (NB > 1 && b1 < B) crow[32] = d[NB - 1];
+          rel = rel_n; pos = pos_n;
+        }
+      } else {
+        for (int e0 = s_lo; e0 < s_hi; e0 += 32) chunk_global(e0, min(32, s_hi - e0), v, g, true);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int b = lane + 32 * nb;
+        if (b < B) {
+          float2 *vp = reinterpret_cast<float2 *>(vs + (size_t)b * p.vstride + jl * OUT);
+#pragma unroll
+          for (int q = 0; q < Q; ++q) vp[q] = g[nb][q];
+        }
+      }
+    }
+    // hubs of the tile: scratch rows only, 32-edge chunks dealt round-robin to the compute warps (their rows of the stage
+    // still hold weight_I: nobody writes g for them)
+    for (unsigned hm = hubs; hm; hm &= hm - 1) {
+      const int jl = __ffs(hm) - 1;
+      const int s_lo = cp[jl], s_hi = cp[jl + 1];
+      float2 v[NB][Q], g[NB][Q];
+      load_v(jl, v);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) g[nb][q] = make_float2(0.f, 0.f);
+      for (int e0 = s_lo + warp * 32; e0 < s_hi; e0 += kCW * 32) chunk_global(e0, min(32, s_hi - e0), v, g, false);
+    }
+    fence_proxy_async();   // g written with generic stores, read by the bulk store; staged data read before the next bulk load
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
+  }
+}
+
+static int g_fused = -1;   // -1: not read yet
+static bool fused_enabled() {
+  if (g_fused < 0) { const char *e = getenv("MRGCN_IDENT_FUSED"); g_fused = (e && e[0] == '0') ? 0 : 1; }
+  return g_fused == 1;
+}
+static int env_int(const char *name, int dflt) { const char *e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
+
+static bool fused_config(FusedCfg &p, int64_t NS, int R, int B, int out, int thresh) {
+  if (B <= 0 || B > 64 || out > 16 || out < 2 || (out & 1)) return false;
+  if (!(out == 4 || out == 8 || out == 10 || out == 12 || out == 16)) return false;
+  if ((NS * out) % 4 != 0 || NS > INT32_MAX) return false;
+  p.comp_bytes = (int)((((size_t)R * B * 4) + 15) & ~(size_t)15);
+  if (p.comp_bytes > 64 * 1024) return false;
+  int tj = env_int("MRGCN_IDF_TJ", (26 * 1024) / (B * out * 4));
+  if (tj > 28) tj = 28;
+  while (tj > 0 && (tj * out) % 4 != 0) --tj;
+  if (tj <= 0 || tj > NS) return false;
+  p.NS = (int)NS; p.R = R; p.B = B; p.out = out; p.TJ = tj; p.thresh = thresh;
+  p.ntiles = (int)cdiv(NS, tj);
+  int mcap = env_int("MRGCN_IDF_MCAP", tj * 16);
+  mcap = mcap < 64 ? 64 : mcap > 1024 ? 1024 : mcap;
+  p.mcap = (mcap + 3) & ~3;
+  const int run = tj * out;
+  p.vstride = ((run / 4) & 1) ? run : run + 4;   // 4 x odd floats: lane-strided 8-byte reads meet 2 banks at most
+  const int tp = (out + 3) & ~3;
+  p.off_v = kHdrInts * 4;
+  p.off_meta = p.off_v + B * p.vstride * 4;
+  p.off_ts = p.off_meta + 4 * (p.mcap + 4) * 4;
+  p.stage_bytes = p.off_ts + p.mcap * tp * 4;
+  const int budget = 227 * 1024 - 256 - p.comp_bytes;
+  int S = budget / p.stage_bytes;
+  const int smax = env_int("MRGCN_IDF_S", 6);
+  if (S > smax) S = smax;
+  if (S > 8) S = 8;
+  if (S < 2) return false;
+  p.S = S;
+  return true;
+}
+
+}  // namespace
+
+// g_weight_I (non-hub sources) and the scratch rows cbuf[e3, :] of every edge; returns 1 when the shape is not handled
+int launch_ident_bwd_fused(const mrgcn_graph *g, const float *V, const float *comp, int B, int out, const float *gact,
+                           float *gW, float *cbuf, cudaStream_t st) {
+  if (!fused_enabled()) return 1;
+  FusedCfg p;
+  const int thresh = g->n_long_cols > 0 ? g->long_col_thresh : 0;
+  if (!fused_config(p, g->NS, g->R, B, out, thresh)) return 1;
+  if (((uintptr_t)V | (uintptr_t)gW) & 15) return 1;
+  const size_t smem = 256 + (size_t)p.comp_bytes + (size_t)p.S * p.stage_bytes;
+  const unsigned grid = (unsigned)(p.ntiles < kNumSMs ? p.ntiles : kNumSMs);
+  const int NB = B > 32 ? 2 : 1;
+  MRGCN_PROF("ident_bwd_fused");
+#define LAUNCH(OUTV, NBV)                                                                                              \
+  do {                                                                                                                 \
+    MRGCN_CUDA(cudaFuncSetAttribute(k_ident_bwd_fused<OUTV, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_ident_bwd_fused<OUTV, NBV><<<grid, kFusedThreads, smem, st>>>(V, comp, g->colptr, g->e2_dst, g->e2_rel, g->e2_val, \
+                                                                    g->e2_to_e3, gact, gW, cbuf, p);                   \
+  } while (0)
+#define LAUNCH_NB(OUTV) \
+  do {                  \
+    if (NB == 2) LAUNCH(OUTV, 2); \
+    else LAUNCH(OUTV, 1);         \
+  } while (0)
+  switch (out) {
+    case 4: LAUNCH_NB(4); break;
+    case 8: LAUNCH_NB(8); break;
+    case 10: LAUNCH_NB(10); break;
+    case 12: LAUNCH_NB(12); break;
+    default: LAUNCH_NB(16); break;
+  }
+#undef LAUNCH_NB
+#undef LAUNCH
+  MRGCN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mrgcn
+
+extern "C" void mrgcn_set_ident_fused(int32_t on) { mrgcn::g_fused = on ? 1 : 0; }

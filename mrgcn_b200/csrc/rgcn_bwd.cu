@@ -425,7 +425,8 @@ __global__ void k_ident_bwd_w_combine(HubSegs h, float *__restrict__ gW, int64_t
 }
 
 // ---- relation-chunk reductions -----------------------------------------------------------------------
-// part[c, b] = sum over the E3 edges of chunk c of cbuf[e3_to_e2[e], b]   (rows of cbuf are B contiguous floats)
+// part[c, b] = sum over the E3 edges of chunk c of cbuf[e3_to_e2[e], b]   (rows of cbuf are B contiguous floats);
+// e3_to_e2 == NULL: the rows are already in E3 order (k_ident_bwd_fused) and are streamed
 __global__ void __launch_bounds__(kThreads)
 k_comp_chunk_reduce(const float *__restrict__ cbuf, const int32_t *__restrict__ chunk_ptr,
                     const int32_t *__restrict__ e3_to_e2, float *__restrict__ part, int B) {
@@ -438,7 +439,7 @@ k_comp_chunk_reduce(const float *__restrict__ cbuf, const int32_t *__restrict__ 
     const int b = b0 + bl;
     double acc = 0.0;
     if (slot < nslots && b < B)
-      for (int e = e_lo + slot; e < e_hi; e += nslots) acc += cbuf[(size_t)e3_to_e2[e] * B + b];
+      for (int e = e_lo + slot; e < e_hi; e += nslots) acc += cbuf[(size_t)(e3_to_e2 ? e3_to_e2[e] : e) * B + b];
     if (slot < nslots) red[slot * bc + bl] = acc;
     __syncthreads();
     for (int s = 1; s < nslots; s <<= 1) {
@@ -448,6 +449,43 @@ k_comp_chunk_reduce(const float *__restrict__ cbuf, const int32_t *__restrict__ 
     if (slot == 0 && b < B) part[(size_t)c * B + b] = (float)red[bl];
     __syncthreads();
   }
+}
+
+// The same sums when the scratch rows already lie in E3 order (k_ident_bwd_fused) and B % 4 == 0: one WARP per chunk streams
+// the chunk's rows with 16-byte loads - lane = (row slot, column group of 4), a slot walks every RS-th row in order, the slots
+// are then added in slot order.  A CTA per chunk (above) is launch- and latency-bound on the many short chunks.
+__global__ void __launch_bounds__(256)
+k_comp_chunk_reduce_rows(const float *__restrict__ cbuf, const int32_t *__restrict__ chunk_ptr, float *__restrict__ part,
+                         int n_chunks, int B) {
+  const int c = (int)(((size_t)blockIdx.x * 256 + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (c >= n_chunks) return;
+  const int G4 = B >> 2, RS = 32 / G4;
+  const int slot = lane / G4, q = lane - slot * G4;
+  const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (slot < RS) {
+    const float4 *base = reinterpret_cast<const float4 *>(cbuf) + q;
+    int e = e_lo + slot;
+    for (; e + 3 * RS < e_hi; e += 4 * RS) {
+      const float4 x0 = __ldcs(base + (size_t)e * G4), x1 = __ldcs(base + (size_t)(e + RS) * G4);
+      const float4 x2 = __ldcs(base + (size_t)(e + 2 * RS) * G4), x3 = __ldcs(base + (size_t)(e + 3 * RS) * G4);
+      a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
+      a0 += x1.x; a1 += x1.y; a2 += x1.z; a3 += x1.w;
+      a0 += x2.x; a1 += x2.y; a2 += x2.z; a3 += x2.w;
+      a0 += x3.x; a1 += x3.y; a2 += x3.z; a3 += x3.w;
+    }
+    for (; e < e_hi; e += RS) {
+      const float4 x0 = __ldcs(base + (size_t)e * G4);
+      a0 += x0.x; a1 += x0.y; a2 += x0.z; a3 += x0.w;
+    }
+  }
+  for (int s = 1; s < RS; ++s) {
+    const int srcl = s * G4 + q;   // < 32 for slot-0 lanes; other lanes read something valid and ignore it
+    const double b0 = __shfl_sync(0xffffffffu, a0, srcl & 31), b1 = __shfl_sync(0xffffffffu, a1, srcl & 31);
+    const double b2 = __shfl_sync(0xffffffffu, a2, srcl & 31), b3 = __shfl_sync(0xffffffffu, a3, srcl & 31);
+    if (slot == 0) { a0 += b0; a1 += b1; a2 += b2; a3 += b3; }
+  }
+  if (slot == 0) reinterpret_cast<float4 *>(part + (size_t)c * B)[q] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
 }
 
 // part[c, k, o] = sum over the E3 edges of chunk c (one relation) of X[j_e, k] * t_e[o]
@@ -689,8 +727,18 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       const int thresh = gI->n_long_cols > 0 ? gI->long_col_thresh : 0;
       TabGeom tg;
       const bool tab_w = f.plan && (mrgcn_tab_mode(B, 0, out) & 2) && tab_geometry(B, out, tg, kBwdWBpt);
+      int tBC0 = 0, tOP0 = 0;
+      const bool tab_c0 = f.plan && (mrgcn_tab_mode(B, 0, out) & 4) && tab_c_geometry(B, out, tBC0, tOP0);
+      // one pass for both gradients (ident_bwd.cu) when neither table kernel is asked for and the shape fits
+      bool fused = false;
+      if (!tab_w && !tab_c0 && a->g_comp_I && a->cbuf && a->part && gI->E > 0) {
+        const int rc = launch_ident_bwd_fused(gI, f.weight_I, f.comp_I, B, out, a->gact, a->g_weight_I, a->cbuf, st);
+        if (rc < 0 || rc > 1) return rc;
+        fused = rc == 0;
+      }
       {  // basis gradient
-        if (tab_w) {
+        if (fused) {
+        } else if (tab_w) {
           if (int rc = launch_tab_bwd_w(gI, f.plan, f.comp_I, B, out, a->gact, a->g_weight_I, st)) return rc;
         } else if (B <= 64 && out <= 256) {
           const int BT = (int)cdiv(B, 8) * 8;
@@ -772,7 +820,9 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
           unsigned grid = 0;
           size_t smem = 0;
           IdentPipe p;
-          if (ident_pipe_config(p, NS, B, out, 0)) {
+          if (fused) {
+            // scratch rows already written, in E3 order
+          } else if (ident_pipe_config(p, NS, B, out, 0)) {
             const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
             smem = 16 * ((2 * p.S * 8 + 15) / 16) + (size_t)p.S * p.stage_bytes;
             MRGCN_PROF("ident_bwd_c");
@@ -821,7 +871,12 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
             MRGCN_LAUNCH_CHECK();
           }
           MRGCN_PROF("comp_chunk_reduce");
-          k_comp_chunk_reduce<<<(unsigned)gI->n_chunks, kThreads, 0, st>>>(a->cbuf, gI->chunk_ptr, gI->e3_to_e2, a->part, B);
+          if (fused && (B & 3) == 0 && B <= 128 && (((uintptr_t)a->cbuf | (uintptr_t)a->part) & 15) == 0)
+            k_comp_chunk_reduce_rows<<<(unsigned)cdiv(gI->n_chunks, 8), 256, 0, st>>>(a->cbuf, gI->chunk_ptr, a->part,
+                                                                                      gI->n_chunks, B);
+          else
+            k_comp_chunk_reduce<<<(unsigned)gI->n_chunks, kThreads, 0, st>>>(a->cbuf, gI->chunk_ptr,
+                                                                             fused ? nullptr : gI->e3_to_e2, a->part, B);
           MRGCN_LAUNCH_CHECK();
         }
         MRGCN_PROF("comp_reduce");

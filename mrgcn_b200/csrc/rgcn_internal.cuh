@@ -94,6 +94,10 @@ int launch_tab_bwd_w(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
                      const float *gact, float *gW, cudaStream_t st);
 int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float *TI, int BI, int out, const float *gact,
                      float *rec, cudaStream_t st);
+// identity-term backward in one pass (ident_bwd.cu): g_weight_I of the non-hub sources + scratch rows cbuf[e3, 0:B] of every
+// edge; returns 1 (nothing launched) when the shape is not handled, 0 when launched, otherwise an error code
+int launch_ident_bwd_fused(const mrgcn_graph *g, const float *V, const float *comp, int B, int out, const float *gact,
+                           float *gW, float *cbuf, cudaStream_t st);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
 struct IdentPipe;

@@ -327,6 +327,8 @@ ORACLE_CASES = [
     # N,   P,  T,     in, out, B,  input, featureless, bias
     (3000, 7, 30000, 0, 16, 0, True, True, True),
     (3002, 7, 30000, 0, 10, 5, True, True, False),
+    (2999, 6, 26000, 0, 16, 40, True, True, True),         # AIFB basis variant: two bases per lane, ragged last tile
+    (2100, 5, 18000, 19, 12, 33, True, False, False),
     (2500, 5, 20000, 33, 10, 4, True, False, True),
     (2500, 5, 20000, 151, 10, 40, True, False, True),
     (2000, 6, 15000, 10, 11, 40, False, False, True),
@@ -338,13 +340,17 @@ ORACLE_CASES = [
 ]
 
 
-@pytest.fixture(params=[1, 7], ids=["tab_fwd", "tab_all"])
+@pytest.fixture(params=[(1, 1), (1, 0), (7, 1)], ids=["tab_fwd", "tab_fwd_split_bwd", "tab_all"])
 def tab_mask(request):
-    """Which table-term kernels (csrc/tab.cu) are on: the default (messages only) and all three."""
+    """Which table-term kernels (csrc/tab.cu) are on: the default (messages only; identity backward in one pass,
+    csrc/ident_bwd.cu), the same with the separate round-1 identity backward kernels, and all three table kernels."""
     from mrgcn_b200 import _native as nv
-    nv.lib().mrgcn_set_tab_mask(request.param)
-    yield request.param
+    mask, fused = request.param
+    nv.lib().mrgcn_set_tab_mask(mask)
+    nv.lib().mrgcn_set_ident_fused(fused)
+    yield mask
     nv.lib().mrgcn_set_tab_mask(-1)
+    nv.lib().mrgcn_set_ident_fused(1)
 
 
 @pytest.mark.parametrize("N,P,T,indim,outdim,B,inp,fl,bias", ORACLE_CASES)
