@@ -11,13 +11,17 @@
 // edge's t_e (broadcast) and comp_I[rel_e, :] (one coalesced row) from shared memory.  The scratch rows are written at
 // the edge's position in the relation-major order E3, so that the per-relation reduction streams them contiguously.
 //
-// One persistent CTA per SM, four roles joined by mbarriers (no CTA-wide barrier after start-up):
-//   loader warp     cp.async.bulk (TMA engine): per tile of TJ sources the B runs weight_I[b, j0 : j0+TJ, :] and the
-//                   tile's slices of e2_dst / e2_rel / e2_val / e2_to_e3 into a ring of S stages
-//   storer warp     when the compute warps are done with a stage it holds g_weight_I of the tile IN PLACE of weight_I
-//                   and goes back to HBM with cp.async.bulk shared -> global (B runs of TJ*out floats: full-line stores)
-//   gather warps    t_e of every staged edge (all gathers of a tile in flight at once) into the stage
-//   compute warps   sources of the tile, handed out by a counter in the stage header
+// One persistent CTA per SM walks tiles of TJ consecutive sources.  Five roles, joined by mbarriers only (no CTA-wide
+// barrier after start-up), over TWO rings of shared memory so that the edge side runs ahead of the table side:
+//   edge ring (Sm slots: header, the tile's slices of e2_dst / e2_rel / e2_val / e2_to_e3, t_e rows)
+//     edge loader    cp.async.bulk (TMA engine) of the four slices; colptr of the tile into the header
+//     gather warps   t_e of every staged edge - all gathers of a tile in flight at once, a few tiles before they are used
+//   table ring (Sv slots: the B runs weight_I[b, j0 : j0+TJ, :])
+//     table loader   cp.async.bulk, one run per basis
+//     compute warps  source jl of the tile belongs to warp jl mod kCW; g_weight_I of the source goes back IN PLACE
+//     storer         a finished slot leaves for HBM with cp.async.bulk shared -> global (B runs: full-line stores)
+// weight_I, g_weight_I and the scratch rows are touched once: they carry the L2 evict-first policy, so that gact (the only
+// re-used operand, ND*out floats) stays L2-resident under 10 GB of streaming traffic.
 // Hub sources (more than `thresh` edges) keep their g_weight_I in k_ident_bwd_w_long (launched afterwards: it overwrites
 // the rows this kernel leaves untouched); their scratch rows are produced here, chunk by chunk across the compute warps.
 // Every sum is taken in edge order by one thread: bit-reproducible, no atomics on floats.
@@ -31,25 +35,62 @@
 namespace mrgcn {
 namespace {
 
-constexpr int kCW = 12;  // compute warps
-constexpr int kGW = 4;   // gather warps
-constexpr int kFusedThreads = (kCW + kGW + 2) * 32;   // + loader + storer
-constexpr int kHdrInts = 64;   // stage header: 0 e_lo, 1 e_hi, 2 j0, 3 a_lo, 4 source counter, 5 hub bits, 16.. colptr[j0 .. j0+TJ]
+constexpr int kCW = 12;  // compute warps (19 warps in all: at most 5 per scheduler, so 96 registers per thread)
+constexpr int kGW = 4;   // gather warps: warp g takes the tiles k = g (mod kGW) whole, so kGW tiles' gathers are in flight
+constexpr int kFusedThreads = (kCW + kGW + 3) * 32;   // + edge loader + table loader + storer
+constexpr int kHdrInts = 64;   // slot header: 0 e_lo, 1 e_hi, 3 a_lo, 5 hub bits, 16.. colptr[j0 .. j0+TJ]
 
 struct FusedCfg {
-  int NS, R, B, out, TJ, S, ntiles, mcap, thresh;
-  int vstride;       // floats between the runs of consecutive bases inside a stage (TJ*out, padded against bank conflicts)
-  int off_v, off_meta, off_ts, stage_bytes;   // byte offsets inside a stage
+  int NS, R, B, out, TJ, Sm, Sv, ntiles, mcap, thresh;
+  int vstride;       // floats between the runs of consecutive bases inside a table slot (TJ*out, padded against bank conflicts)
+  int off_meta, off_ts, mslot_bytes, vslot_bytes;
   int comp_bytes;
+  int dbg;   // MRGCN_IDF_DBG (timing experiments only, results are wrong): 1 no scratch-row stores, 2 no gact gathers, 4 no bulk stores
 };
 
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+// position in a ring of S slots: slot index and phase parity of its current use, advanced without divisions
+struct RingPos {
+  int s, S;
+  uint32_t ph;
+  __device__ __forceinline__ RingPos(int S_, int k0 = 0) : s(0), S(S_), ph(0) { advance(k0); }
+  __device__ __forceinline__ void advance(int n = 1) {
+    s += n;
+    while (s >= S) { s -= S; ph ^= 1; }
+  }
+};
+
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst, const void *src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src)),
+               "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stg_hint(float *p, float v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float2 ldg2_hint(const float2 *p, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 
 // one edge: the warp's lanes hold v (rows of weight_I) and g (accumulators) of NB bases each
 template <int OUT, int NB>
@@ -77,41 +118,45 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
   constexpr int TP = (OUT + 3) & ~3;   // floats per staged t_e row
   constexpr int Q = OUT / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-  uint64_t *tready = full + p.S;
-  uint64_t *done = tready + p.S;
-  uint64_t *freeb = done + p.S;
+  const int Sm = p.Sm, Sv = p.Sv;
+  uint64_t *mfull = reinterpret_cast<uint64_t *>(smem_raw);   // edge slices landed (tx count)
+  uint64_t *tready = mfull + Sm;                               // t_e rows written (by the tile's gather warp)
+  uint64_t *mdone = tready + Sm;                               // edge slot drained (one arrival per compute warp)
+  uint64_t *vfull = mdone + Sm;                                // table runs landed (tx count)
+  uint64_t *vdone = vfull + Sv;                                // g_weight_I of the tile complete (one arrival per compute warp)
+  uint64_t *vfree = vdone + Sv;                                // bulk store has read the slot
   float *comp_s = reinterpret_cast<float *>(smem_raw + 256);
-  unsigned char *stages = smem_raw + 256 + p.comp_bytes;
+  unsigned char *mslots = smem_raw + 256 + p.comp_bytes;
+  unsigned char *vslots = mslots + (size_t)Sm * p.mslot_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int B = p.B, S = p.S, TJ = p.TJ;
+  const int B = p.B, TJ = p.TJ;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&tready[s], kGW); mbar_init(&done[s], kCW); mbar_init(&freeb[s], 1); }
+    for (int s = 0; s < Sm; ++s) { mbar_init(&mfull[s], 1); mbar_init(&tready[s], 1); mbar_init(&mdone[s], kCW); }
+    for (int s = 0; s < Sv; ++s) { mbar_init(&vfull[s], 1); mbar_init(&vdone[s], kCW); mbar_init(&vfree[s], 1); }
     mbar_fence_init();
   }
   for (int x = threadIdx.x; x < p.R * B; x += kFusedThreads) comp_s[x] = __ldg(comp + x);
   __syncthreads();
   const int ntiles_mine = (int)blockIdx.x < p.ntiles ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto tile_j0 = [&](int k) {
+    int j0 = ((int)blockIdx.x + k * (int)gridDim.x) * TJ;
+    return j0 + TJ > p.NS ? p.NS - TJ : j0;   // the last tile overlaps its neighbour: the same values are written twice
+  };
+  const uint32_t run_bytes = (uint32_t)TJ * OUT * 4;
 
   if (warp == kCW + kGW) {
-    // ============================== loader: weight_I runs + edge metadata of tile k into stage k % S ==============================
-    const uint32_t run_bytes = (uint32_t)TJ * OUT * 4;
-    auto tile_j0 = [&](int k) {
-      int j0 = ((int)blockIdx.x + k * (int)gridDim.x) * TJ;
-      return j0 + TJ > p.NS ? p.NS - TJ : j0;   // the last tile overlaps its neighbour: the same values are written twice
-    };
+    // ============================== edge loader ==============================
     int cpv = 0;   // colptr[j0 + lane] of the next tile: loaded one tile ahead, off the critical path
     if (ntiles_mine > 0 && lane <= TJ) cpv = colptr[tile_j0(0) + lane];
-    for (int k = 0; k < ntiles_mine; ++k) {
-      const int s = k % S;
-      unsigned char *st = stages + (size_t)s * p.stage_bytes;
+    RingPos r(Sm);
+    for (int k = 0; k < ntiles_mine; ++k, r.advance()) {
+      const int s = r.s;
+      unsigned char *st = mslots + (size_t)s * p.mslot_bytes;
       int *hdr = reinterpret_cast<int *>(st);
-      float *vs = reinterpret_cast<float *>(st + p.off_v);
-      const int j0 = tile_j0(k);
       const int cur = cpv;
       if (k + 1 < ntiles_mine && lane <= TJ) cpv = colptr[tile_j0(k + 1) + lane];
-      if (k >= S) mbar_wait(&freeb[s], ((k / S) - 1) & 1, 7);   // the stage's previous tile has left for HBM
+      if (k >= Sm) mbar_wait(&mdone[s], r.ph ^ 1, 7, 64);
       const int e_lo = __shfl_sync(0xffffffffu, cur, 0), e_hi = __shfl_sync(0xffffffffu, cur, TJ);
       const int nxt = __shfl_down_sync(0xffffffffu, cur, 1);
       const unsigned hubs = __ballot_sync(0xffffffffu, lane < TJ && p.thresh > 0 && nxt - cur > p.thresh);
@@ -122,39 +167,53 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       int *mD = reinterpret_cast<int *>(st + p.off_meta);
       __syncwarp();
       if (lane == 0) {
-        hdr[0] = e_lo; hdr[1] = e_hi; hdr[2] = j0; hdr[3] = a_lo; hdr[4] = 0; hdr[5] = (int)hubs;
+        hdr[0] = e_lo; hdr[1] = e_hi; hdr[3] = a_lo; hdr[5] = (int)hubs;
         fence_proxy_async();
-        mbar_expect_tx(&full[s], run_bytes * B + 4u * cnt * 4u);
+        mbar_expect_tx(&mfull[s], 4u * cnt * 4u);
       }
       __syncwarp();
-      for (int b = lane; b < B; b += 32)
-        bulk_g2s(vs + (size_t)b * p.vstride, V + ((size_t)b * p.NS + j0) * OUT, run_bytes, &full[s]);
       if (cnt > 0) {
         const int ms = p.mcap + 4;
-        if (lane == 28) bulk_g2s(mD, e2_dst + a_lo, cnt * 4u, &full[s]);
-        if (lane == 29) bulk_g2s(mD + ms, e2_rel + a_lo, cnt * 4u, &full[s]);
-        if (lane == 30) bulk_g2s(mD + 2 * ms, e2_val + a_lo, cnt * 4u, &full[s]);
-        if (lane == 31) bulk_g2s(mD + 3 * ms, e2_to_e3 + a_lo, cnt * 4u, &full[s]);
+        if (lane == 0) bulk_g2s(mD, e2_dst + a_lo, cnt * 4u, &mfull[s]);
+        if (lane == 1) bulk_g2s(mD + ms, e2_rel + a_lo, cnt * 4u, &mfull[s]);
+        if (lane == 2) bulk_g2s(mD + 2 * ms, e2_val + a_lo, cnt * 4u, &mfull[s]);
+        if (lane == 3) bulk_g2s(mD + 3 * ms, e2_to_e3 + a_lo, cnt * 4u, &mfull[s]);
       }
     }
     return;
   }
   if (warp == kCW + kGW + 1) {
-    // ============================== storer: a finished stage holds g_weight_I of its tile ==============================
-    const uint32_t run_bytes = (uint32_t)TJ * OUT * 4;
-    for (int k = 0; k < ntiles_mine; ++k) {
-      const int s = k % S;
-      unsigned char *st = stages + (size_t)s * p.stage_bytes;
-      const int *hdr = reinterpret_cast<const int *>(st);
-      const float *vs = reinterpret_cast<const float *>(st + p.off_v);
-      mbar_wait(&done[s], (k / S) & 1, 8);
-      const int j0 = hdr[2];
+    // ============================== table loader ==============================
+    const uint64_t pol = policy_evict_first();
+    RingPos r(Sv);
+    for (int k = 0; k < ntiles_mine; ++k, r.advance()) {
+      const int s = r.s;
+      float *vs = reinterpret_cast<float *>(vslots + (size_t)s * p.vslot_bytes);
+      const int j0 = tile_j0(k);
+      if (k >= Sv) mbar_wait(&vfree[s], r.ph ^ 1, 8, 64);   // the slot's previous tile has left for HBM
+      if (lane == 0) mbar_expect_tx(&vfull[s], run_bytes * B);
+      __syncwarp();
       for (int b = lane; b < B; b += 32)
-        bulk_s2g(gW + ((size_t)b * p.NS + j0) * OUT, vs + (size_t)b * p.vstride, run_bytes);
+        bulk_g2s_hint(vs + (size_t)b * p.vstride, V + ((size_t)b * p.NS + j0) * OUT, run_bytes, &vfull[s], pol);
+    }
+    return;
+  }
+  if (warp == kCW + kGW + 2) {
+    // ============================== storer ==============================
+    const uint64_t pol = policy_evict_first();
+    RingPos r(Sv);
+    for (int k = 0; k < ntiles_mine; ++k, r.advance()) {
+      const int s = r.s;
+      const float *vs = reinterpret_cast<const float *>(vslots + (size_t)s * p.vslot_bytes);
+      const int j0 = tile_j0(k);
+      mbar_wait(&vdone[s], r.ph, 9, 64);
+      if (!(p.dbg & 4))
+        for (int b = lane; b < B; b += 32)
+          bulk_s2g_hint(gW + ((size_t)b * p.NS + j0) * OUT, vs + (size_t)b * p.vstride, run_bytes, pol);
       bulk_commit();
       bulk_wait_read0();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&freeb[s]);
+      if (lane == 0) mbar_arrive(&vfree[s]);
     }
     bulk_wait0();
     return;
@@ -163,10 +222,18 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
   if (warp >= kCW) {
     // ============================== gather warps: t_e of the staged edges ==============================
     const int gw = warp - kCW;
-    for (int k = 0; k < ntiles_mine; ++k) {
-      const int s = k % S;
-      mbar_wait(&full[s], (k / S) & 1, 1);
-      unsigned char *st = stages + (size_t)s * p.stage_bytes;
+    const uint64_t keep = policy_evict_last();
+    RingPos r(Sm);
+    int mine = gw;   // tiles until this warp's next one
+    for (int k = 0; k < ntiles_mine; ++k, r.advance()) {
+      const int s = r.s;
+      // Every gather warp waits for every tile, in order, although it gathers only its own: a parity wait cannot tell phase n
+      // from phase n +- 2, so a waiter must never be more than one phase away from the barrier - a warp that skipped the
+      // slot's previous use could find the barrier still in that phase (wait passes at once, on stale data).
+      mbar_wait(&mfull[s], r.ph, 1, 32);
+      if (mine > 0) { --mine; continue; }
+      mine = kGW - 1;
+      unsigned char *st = mslots + (size_t)s * p.mslot_bytes;
       const int *hdr = reinterpret_cast<const int *>(st);
       const int e_lo = hdr[0], e_hi = hdr[1], a_lo = hdr[3];
       const int ms = p.mcap + 4;
@@ -174,17 +241,37 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       const float *mV = reinterpret_cast<const float *>(mD + 2 * ms);
       float *Ts = reinterpret_cast<float *>(st + p.off_ts);
       const int n_st = min(e_hi - a_lo, p.mcap);
-      for (int idx = (e_lo - a_lo) + gw * 32 + lane; idx < n_st; idx += kGW * 32) {
-        const float val = mV[idx];
-        const float2 *gp = reinterpret_cast<const float2 *>(gact + (size_t)mD[idx] * OUT);
-        float r[TP];
+      // four edges per lane and trip (128 per warp): their gathers are in flight together
+      constexpr int U = 4;
+      for (int i0 = (e_lo - a_lo) + lane; i0 < n_st; i0 += U * 32) {
+        float r_[U][TP];
+        float val[U];
+        const float2 *gp[U];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) { float2 x = __ldg(gp + q); r[2 * q] = val * x.x; r[2 * q + 1] = val * x.y; }
+        for (int u = 0; u < U; ++u) {
+          const int idx = i0 + 32 * u < n_st ? i0 + 32 * u : i0;
+          val[u] = mV[idx];
+          gp[u] = reinterpret_cast<const float2 *>(gact + (size_t)mD[idx] * OUT);
+        }
 #pragma unroll
-        for (int q = OUT; q < TP; ++q) r[q] = 0.f;
-        float4 *dst = reinterpret_cast<float4 *>(Ts + (size_t)idx * TP);
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int q = 0; q < TP / 4; ++q) dst[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          for (int q = 0; q < Q; ++q) {
+            float2 x = (p.dbg & 2) ? make_float2(1.f, 2.f) : ldg2_hint(gp[u] + q, keep);
+            r_[u][2 * q] = x.x; r_[u][2 * q + 1] = x.y;
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (i0 + 32 * u < n_st) {
+#pragma unroll
+            for (int q = 0; q < OUT; ++q) r_[u][q] *= val[u];
+#pragma unroll
+            for (int q = OUT; q < TP; ++q) r_[u][q] = 0.f;
+            float4 *dst = reinterpret_cast<float4 *>(Ts + (size_t)(i0 + 32 * u) * TP);
+#pragma unroll
+            for (int q = 0; q < TP / 4; ++q) dst[q] = make_float4(r_[u][4 * q], r_[u][4 * q + 1], r_[u][4 * q + 2], r_[u][4 * q + 3]);
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&tready[s]);
@@ -194,23 +281,25 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
 
   // ============================== compute warps ==============================
   const int b0 = lane, b1 = lane + 32;
-  for (int k = 0; k < ntiles_mine; ++k) {
-    const int s = k % S;
-    mbar_wait(&full[s], (k / S) & 1, 2);
-    mbar_wait(&tready[s], (k / S) & 1, 3);
-    unsigned char *st = stages + (size_t)s * p.stage_bytes;
-    int *hdr = reinterpret_cast<int *>(st);
+  const uint64_t pol = policy_evict_first();
+  RingPos rm(Sm), rv(Sv);
+  for (int k = 0; k < ntiles_mine; ++k, rm.advance(), rv.advance()) {
+    const int sm = rm.s, sv = rv.s;
+    mbar_wait(&tready[sm], rm.ph, 3);   // implies mfull (the tile's gather warp waited for it)
+    mbar_wait(&vfull[sv], rv.ph, 2);
+    unsigned char *st = mslots + (size_t)sm * p.mslot_bytes;
+    const int *hdr = reinterpret_cast<const int *>(st);
     const int a_lo = hdr[3];
     const unsigned hubs = (unsigned)hdr[5];
     const int *cp = hdr + 16;
-    float *vs = reinterpret_cast<float *>(st + p.off_v);
+    float *vs = reinterpret_cast<float *>(vslots + (size_t)sv * p.vslot_bytes);
     const int ms = p.mcap + 4;
     const int *mD = reinterpret_cast<const int *>(st + p.off_meta);
     const int *mR = mD + ms;
     const int *mP = mD + 3 * ms;
     const float *Ts = reinterpret_cast<const float *>(st + p.off_ts);
 
-    // v/g of one source: v from the stage, g back into the same place
+    // v/g of one source: v from the table slot, g back into the same place
     auto load_v = [&](int jl, float2 (&v)[NB][Q]) {
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
@@ -245,16 +334,12 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
         for (int nb = 0; nb < NB; ++nb) c[nb] = (lane + 32 * nb < B) ? comp_s[rel * B + lane + 32 * nb] : 0.f;
         edge_body<OUT, NB>(t, c, v, g, d, do_g);
         float *crow = cbuf + (size_t)pos * B;
-        if (b0 < B) crow[b0] = d[0];
-        if (NB > 1 && b1 < B) crow[b1] = d[NB - 1];
+        if (b0 < B) stg_hint(crow + b0, d[0], pol);
+        if (NB > 1 && b1 < B) stg_hint(crow + b1, d[NB - 1], pol);
       }
     };
 
-    for (;;) {
-      int jl = 0;
-      if (lane == 0) jl = atomicAdd(&hdr[4], 1);
-      jl = __shfl_sync(0xffffffffu, jl, 0);
-      if (jl >= TJ) break;
+    for (int jl = warp; jl < TJ; jl += kCW) {
       if ((hubs >> jl) & 1u) continue;   // hub: see below
       const int s_lo = cp[jl], s_hi = cp[jl + 1];
       float2 v[NB][Q], g[NB][Q];
@@ -286,8 +371,10 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
           for (int nb = 0; nb < NB; ++nb) c[nb] = (lane + 32 * nb < B) ? cr[32 * nb] : 0.f;
           edge_body<OUT, NB>(t, c, v, g, d, true);
           float *crow = cb + (size_t)pos * B;
-          if (b0 < B) crow[0] = d[0];
-          if (NB > 1 && b1 < B) crow[32] = d[NB - 1];
+          if (!(p.dbg & 1)) {
+            if (b0 < B) stg_hint(crow, d[0], pol);
+            if (NB > 1 && b1 < B) stg_hint(crow + 32, d[NB - 1], pol);
+          }
           rel = rel_n; pos = pos_n;
         }
       } else {
@@ -303,7 +390,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
         }
       }
     }
-    // hubs of the tile: scratch rows only, 32-edge chunks dealt round-robin to the compute warps (their rows of the stage
+    // hubs of the tile: scratch rows only, 32-edge chunks dealt round-robin to the compute warps (their rows of the slot
     // still hold weight_I: nobody writes g for them)
     for (unsigned hm = hubs; hm; hm &= hm - 1) {
       const int jl = __ffs(hm) - 1;
@@ -318,7 +405,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
     }
     fence_proxy_async();   // g written with generic stores, read by the bulk store; staged data read before the next bulk load
     __syncwarp();
-    if (lane == 0) mbar_arrive(&done[s]);
+    if (lane == 0) { mbar_arrive(&vdone[sv]); mbar_arrive(&mdone[sm]); }
   }
 }
 
@@ -330,7 +417,7 @@ static bool fused_enabled() {
 static int env_int(const char *name, int dflt) { const char *e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 
 static bool fused_config(FusedCfg &p, int64_t NS, int R, int B, int out, int thresh) {
-  if (B <= 0 || B > 64 || out > 16 || out < 2 || (out & 1)) return false;
+  if (B <= 0 || B > 64) return false;
   if (!(out == 4 || out == 8 || out == 10 || out == 12 || out == 16)) return false;
   if ((NS * out) % 4 != 0 || NS > INT32_MAX) return false;
   p.comp_bytes = (int)((((size_t)R * B * 4) + 15) & ~(size_t)15);
@@ -338,6 +425,11 @@ static bool fused_config(FusedCfg &p, int64_t NS, int R, int B, int out, int thr
   int tj = env_int("MRGCN_IDF_TJ", (26 * 1024) / (B * out * 4));
   if (tj > 28) tj = 28;
   while (tj > 0 && (tj * out) % 4 != 0) --tj;
+  if (tj >= kCW) {   // whole rounds of the compute warps (source jl belongs to warp jl mod kCW)
+    int m = (tj / kCW) * kCW;
+    while (m > 0 && (m * out) % 4 != 0) m -= kCW;
+    if (m > 0) tj = m;
+  }
   if (tj <= 0 || tj > NS) return false;
   p.NS = (int)NS; p.R = R; p.B = B; p.out = out; p.TJ = tj; p.thresh = thresh;
   p.ntiles = (int)cdiv(NS, tj);
@@ -347,17 +439,22 @@ static bool fused_config(FusedCfg &p, int64_t NS, int R, int B, int out, int thr
   const int run = tj * out;
   p.vstride = ((run / 4) & 1) ? run : run + 4;   // 4 x odd floats: lane-strided 8-byte reads meet 2 banks at most
   const int tp = (out + 3) & ~3;
-  p.off_v = kHdrInts * 4;
-  p.off_meta = p.off_v + B * p.vstride * 4;
+  p.off_meta = kHdrInts * 4;
   p.off_ts = p.off_meta + 4 * (p.mcap + 4) * 4;
-  p.stage_bytes = p.off_ts + p.mcap * tp * 4;
+  p.mslot_bytes = p.off_ts + p.mcap * tp * 4;
+  p.vslot_bytes = B * p.vstride * 4;
   const int budget = 227 * 1024 - 256 - p.comp_bytes;
-  int S = budget / p.stage_bytes;
-  const int smax = env_int("MRGCN_IDF_S", 6);
-  if (S > smax) S = smax;
-  if (S > 8) S = 8;
-  if (S < 2) return false;
-  p.S = S;
+  // table ring first (it carries the HBM traffic), the edge ring gets the rest: it should be the deeper one
+  int sv = env_int("MRGCN_IDF_SV", 4), sm = env_int("MRGCN_IDF_SM", 0);
+  if (sv > 5) sv = 5;
+  while (sv >= 2 && budget - sv * p.vslot_bytes < 2 * p.mslot_bytes) --sv;
+  if (sv < 2) return false;
+  const int sm_max = (budget - sv * p.vslot_bytes) / p.mslot_bytes;
+  if (sm <= 0 || sm > sm_max) sm = sm_max;
+  if (sm > 5) sm = 5;   // 3*Sm + 3*Sv barriers in the first 256 bytes
+  if (sm < 2) return false;
+  p.dbg = env_int("MRGCN_IDF_DBG", 0);
+  p.Sv = sv; p.Sm = sm;   // (fewer edge slots than gather warps only serialises the gather warps)
   return true;
 }
 
@@ -371,8 +468,10 @@ int launch_ident_bwd_fused(const mrgcn_graph *g, const float *V, const float *co
   const int thresh = g->n_long_cols > 0 ? g->long_col_thresh : 0;
   if (!fused_config(p, g->NS, g->R, B, out, thresh)) return 1;
   if (((uintptr_t)V | (uintptr_t)gW) & 15) return 1;
-  const size_t smem = 256 + (size_t)p.comp_bytes + (size_t)p.S * p.stage_bytes;
-  const unsigned grid = (unsigned)(p.ntiles < kNumSMs ? p.ntiles : kNumSMs);
+  const size_t smem = 256 + (size_t)p.comp_bytes + (size_t)p.Sm * p.mslot_bytes + (size_t)p.Sv * p.vslot_bytes;
+  // MRGCN_IDF_GRID: fewer CTAs than SMs, so that small test graphs also walk many tiles per CTA (ring wrap-around)
+  const int gmax = env_int("MRGCN_IDF_GRID", kNumSMs);
+  const unsigned grid = (unsigned)(p.ntiles < gmax ? p.ntiles : gmax);
   const int NB = B > 32 ? 2 : 1;
   MRGCN_PROF("ident_bwd_fused");
 #define LAUNCH(OUTV, NBV)                                                                                              \
