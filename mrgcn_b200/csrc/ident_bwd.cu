@@ -45,7 +45,7 @@ struct FusedCfg {
   int vstride;       // floats between the runs of consecutive bases inside a table slot (TJ*out, padded against bank conflicts)
   int off_meta, off_ts, mslot_bytes, vslot_bytes;
   int comp_bytes;
-  int dbg;   // MRGCN_IDF_DBG (timing experiments only, results are wrong): 1 no scratch-row stores, 2 no gact gathers, 4 no bulk stores
+  int dbg;   // MRGCN_IDF_DBG (timing experiments only, results are wrong): 1 no scratch-row stores, 2 no gact gathers, 4 no bulk stores, 8 compute warps idle, 16 one bulk load per tile
 };
 
 // position in a ring of S slots: slot index and phase parity of its current use, advanced without divisions
@@ -193,6 +193,9 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       if (k >= Sv) mbar_wait(&vfree[s], r.ph ^ 1, 8, 64);   // the slot's previous tile has left for HBM
       if (lane == 0) mbar_expect_tx(&vfull[s], run_bytes * B);
       __syncwarp();
+      if (p.dbg & 16) {
+        if (lane == 0) bulk_g2s_hint(vs, V + (size_t)j0 * OUT * B, run_bytes * B, &vfull[s], pol);
+      } else
       for (int b = lane; b < B; b += 32)
         bulk_g2s_hint(vs + (size_t)b * p.vstride, V + ((size_t)b * p.NS + j0) * OUT, run_bytes, &vfull[s], pol);
     }
@@ -340,6 +343,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
     };
 
     for (int jl = warp; jl < TJ; jl += kCW) {
+      if (p.dbg & 8) break;
       if ((hubs >> jl) & 1u) continue;   // hub: see below
       const int s_lo = cp[jl], s_hi = cp[jl + 1];
       float2 v[NB][Q], g[NB][Q];
@@ -392,7 +396,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
     }
     // hubs of the tile: scratch rows only, 32-edge chunks dealt round-robin to the compute warps (their rows of the slot
     // still hold weight_I: nobody writes g for them)
-    for (unsigned hm = hubs; hm; hm &= hm - 1) {
+    for (unsigned hm = (p.dbg & 8) ? 0u : hubs; hm; hm &= hm - 1) {
       const int jl = __ffs(hm) - 1;
       const int s_lo = cp[jl], s_hi = cp[jl + 1];
       float2 v[NB][Q], g[NB][Q];
