@@ -18,7 +18,7 @@
 //     gather warps   t_e of every staged edge - all gathers of a tile in flight at once, a few tiles before they are used
 //   table ring (Sv slots: the B runs weight_I[b, j0 : j0+TJ, :])
 //     table loader   cp.async.bulk, one run per basis
-//     compute warps  source jl of the tile belongs to warp jl mod kCW; g_weight_I of the source goes back IN PLACE
+//     compute warps  sources of the tile, claimed from a counter in the slot header; g_weight_I goes back IN PLACE
 //     storer         a finished slot leaves for HBM with cp.async.bulk shared -> global (B runs: full-line stores)
 // weight_I, g_weight_I and the scratch rows are touched once: they carry the L2 evict-first policy, so that gact (the only
 // re-used operand, ND*out floats) stays L2-resident under 10 GB of streaming traffic.
@@ -38,14 +38,14 @@ namespace {
 constexpr int kCW = 12;  // compute warps (19 warps in all: at most 5 per scheduler, so 96 registers per thread)
 constexpr int kGW = 4;   // gather warps: warp g takes the tiles k = g (mod kGW) whole, so kGW tiles' gathers are in flight
 constexpr int kFusedThreads = (kCW + kGW + 3) * 32;   // + edge loader + table loader + storer
-constexpr int kHdrInts = 64;   // slot header: 0 e_lo, 1 e_hi, 3 a_lo, 5 hub bits, 16.. colptr[j0 .. j0+TJ]
+constexpr int kHdrInts = 64;   // slot header: 0 e_lo, 1 e_hi, 3 a_lo, 4 source counter, 5 hub bits, 16.. colptr[j0 .. j0+TJ]
 
 struct FusedCfg {
   int NS, R, B, out, TJ, Sm, Sv, ntiles, mcap, thresh;
   int vstride;       // floats between the runs of consecutive bases inside a table slot (TJ*out, padded against bank conflicts)
   int off_meta, off_ts, mslot_bytes, vslot_bytes;
   int comp_bytes;
-  int dbg;   // MRGCN_IDF_DBG (timing experiments only, results are wrong): 1 no scratch-row stores, 2 no gact gathers, 4 no bulk stores, 8 compute warps idle, 16 one bulk load per tile
+  int dbg;   // MRGCN_IDF_DBG (timing experiments only, results are wrong): (1 unused) 2 no gact gathers, 4 no bulk stores, 8 compute warps idle, 16 one bulk load per tile
 };
 
 // position in a ring of S slots: slot index and phase parity of its current use, advanced without divisions
@@ -109,7 +109,7 @@ __device__ __forceinline__ void edge_body(const float2 (&t)[OUT / 2], const floa
   }
 }
 
-template <int OUT, int NB>
+template <int OUT, int NB, int NG>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, const int32_t *__restrict__ colptr,
                   const int32_t *__restrict__ e2_dst, const int32_t *__restrict__ e2_rel, const float *__restrict__ e2_val,
@@ -156,7 +156,10 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       int *hdr = reinterpret_cast<int *>(st);
       const int cur = cpv;
       if (k + 1 < ntiles_mine && lane <= TJ) cpv = colptr[tile_j0(k + 1) + lane];
-      if (k >= Sm) mbar_wait(&mdone[s], r.ph ^ 1, 7, 64);
+      if (k >= Sm) {
+        mbar_wait(&mdone[s], r.ph ^ 1, 7, 64);
+        fence_proxy_async();   // the slot's generic reads (acquired above) before the async-proxy writes below
+      }
       const int e_lo = __shfl_sync(0xffffffffu, cur, 0), e_hi = __shfl_sync(0xffffffffu, cur, TJ);
       const int nxt = __shfl_down_sync(0xffffffffu, cur, 1);
       const unsigned hubs = __ballot_sync(0xffffffffu, lane < TJ && p.thresh > 0 && nxt - cur > p.thresh);
@@ -167,7 +170,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       int *mD = reinterpret_cast<int *>(st + p.off_meta);
       __syncwarp();
       if (lane == 0) {
-        hdr[0] = e_lo; hdr[1] = e_hi; hdr[3] = a_lo; hdr[5] = (int)hubs;
+        hdr[0] = e_lo; hdr[1] = e_hi; hdr[3] = a_lo; hdr[4] = 0; hdr[5] = (int)hubs;
         fence_proxy_async();
         mbar_expect_tx(&mfull[s], 4u * cnt * 4u);
       }
@@ -190,7 +193,10 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       const int s = r.s;
       float *vs = reinterpret_cast<float *>(vslots + (size_t)s * p.vslot_bytes);
       const int j0 = tile_j0(k);
-      if (k >= Sv) mbar_wait(&vfree[s], r.ph ^ 1, 8, 64);   // the slot's previous tile has left for HBM
+      if (k >= Sv) {
+        mbar_wait(&vfree[s], r.ph ^ 1, 8, 64);   // the slot's previous tile has left for HBM
+        fence_proxy_async();
+      }
       if (lane == 0) mbar_expect_tx(&vfull[s], run_bytes * B);
       __syncwarp();
       if (p.dbg & 16) {
@@ -210,6 +216,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       const float *vs = reinterpret_cast<const float *>(vslots + (size_t)s * p.vslot_bytes);
       const int j0 = tile_j0(k);
       mbar_wait(&vdone[s], r.ph, 9, 64);
+      fence_proxy_async();   // the compute warps' generic writes of g (acquired above) before the async-proxy reads below
       if (!(p.dbg & 4))
         for (int b = lane; b < B; b += 32)
           bulk_s2g_hint(gW + ((size_t)b * p.NS + j0) * OUT, vs + (size_t)b * p.vstride, run_bytes, pol);
@@ -284,6 +291,12 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
 
   // ============================== compute warps ==============================
   const int b0 = lane, b1 = lane + 32;
+  // B > 32: the bases 32 .. B-1 keep only B - 32 lanes busy.  The staged loop therefore takes them for `ng` edges at a time:
+  // lane group qg (gs lanes) works on edge i + qg, lane li of the group on basis 32 + li.  Every group then holds a partial
+  // g_weight_I of those bases (edges i = qg mod ng); the groups are added at the end of the source in a fixed butterfly.
+  constexpr int ng = NG, gs = 32 / NG;   // NG = 4 for B <= 40, 2 for B <= 48, else 1 (the host picks the instance)
+  const int qg = lane / gs, li = lane & (gs - 1);
+  const int bb = 32 + li;
   const uint64_t pol = policy_evict_first();
   RingPos rm(Sm), rv(Sv);
   for (int k = 0; k < ntiles_mine; ++k, rm.advance(), rv.advance()) {
@@ -306,7 +319,7 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
     auto load_v = [&](int jl, float2 (&v)[NB][Q]) {
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        const int b = lane + 32 * nb;
+        const int b = nb == 0 ? lane : bb;   // second set: every lane group holds the same rows 32 .. B-1
         const float2 *vp = reinterpret_cast<const float2 *>(vs + (size_t)b * p.vstride + jl * OUT);
 #pragma unroll
         for (int q = 0; q < Q; ++q) v[nb][q] = b < B ? vp[q] : make_float2(0.f, 0.f);
@@ -342,8 +355,16 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
       }
     };
 
-    for (int jl = warp; jl < TJ; jl += kCW) {
+    // Sources are claimed from a counter in the slot header, not dealt out by warp index: source lengths are heavy-tailed,
+    // and with a fixed deal the slowest of the kCW warps held every slot of the (short) ring - the others waited for
+    // slots about half of the time.  A warp that finds the counter exhausted moves on to the next tile.
+    int *ctr = const_cast<int *>(hdr) + 4;
+    for (;;) {
       if (p.dbg & 8) break;
+      int jl = 0;
+      if (lane == 0) jl = atomicAdd(ctr, 1);
+      jl = __shfl_sync(0xffffffffu, jl, 0);
+      if (jl >= TJ) break;
       if ((hubs >> jl) & 1u) continue;   // hub: see below
       const int s_lo = cp[jl], s_hi = cp[jl + 1];
       float2 v[NB][Q], g[NB][Q];
@@ -359,35 +380,79 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
         const float *tptr = Ts + (size_t)(s_lo - a_lo) * TP;
         const float *cl = comp_s + lane;
         float *cb = cbuf + lane;
-        int rel = rp[0], pos = pp[0];
-        for (int n = s_hi - s_lo; n > 0; --n) {
-          ++rp; ++pp;
-          const int rel_n = rp[0], pos_n = pp[0];
-          float2 t[Q];
-          const float4 *tp = reinterpret_cast<const float4 *>(tptr);
+        auto load_t = [&](const float *tq, float2 (&t)[Q]) {
+          const float4 *tp = reinterpret_cast<const float4 *>(tq);
 #pragma unroll
           for (int q = 0; q < Q / 2; ++q) { float4 x = tp[q]; t[2 * q] = make_float2(x.x, x.y); t[2 * q + 1] = make_float2(x.z, x.w); }
-          if constexpr (OUT % 4 != 0) t[Q - 1] = *reinterpret_cast<const float2 *>(tptr + OUT - 2);
-          tptr += TP;
-          float c[NB], d[NB];
-          const float *cr = cl + rel * B;
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) c[nb] = (lane + 32 * nb < B) ? cr[32 * nb] : 0.f;
-          edge_body<OUT, NB>(t, c, v, g, d, true);
-          float *crow = cb + (size_t)pos * B;
-          if (!(p.dbg & 1)) {
-            if (b0 < B) stg_hint(crow, d[0], pol);
-            if (NB > 1 && b1 < B) stg_hint(crow + 32, d[NB - 1], pol);
+          if constexpr (OUT % 4 != 0) t[Q - 1] = *reinterpret_cast<const float2 *>(tq + OUT - 2);
+        };
+        if constexpr (NB == 1) {
+          int rel = rp[0], pos = pp[0];
+          for (int n = s_hi - s_lo; n > 0; --n) {
+            ++rp; ++pp;
+            const int rel_n = rp[0], pos_n = pp[0];
+            float2 t[Q];
+            load_t(tptr, t);
+            tptr += TP;
+            float c[NB], d[NB];
+            c[0] = (lane < B) ? cl[rel * B] : 0.f;
+            edge_body<OUT, NB>(t, c, v, g, d, true);
+            if (b0 < B) stg_hint(cb + (size_t)pos * B, d[0], pol);
+            rel = rel_n; pos = pos_n;
           }
-          rel = rel_n; pos = pos_n;
+        } else {
+          const int n = s_hi - s_lo;
+          for (int i = 0; i < n; i += ng) {
+            const int m = min(ng, n - i);
+            // bases 0 .. 31: one edge at a time, t_e broadcast
+#pragma unroll
+            for (int u = 0; u < NG; ++u) {
+              if (u >= m) break;
+              const int rel = rp[u], pos = pp[u];
+              float2 t[Q];
+              load_t(tptr + u * TP, t);
+              const float c0 = cl[rel * B];
+              float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) fma2v(a2, v[0][q], t[q]);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) fma2(g[0][q], c0, t[q]);
+              stg_hint(cb + (size_t)pos * B, a2.x + a2.y, pol);
+            }
+            // bases 32 .. B-1: lane group qg takes edge i + qg
+            {
+              const bool on = qg < m && bb < B;
+              const int u = qg < m ? qg : 0;
+              const int rel = rp[u], pos = pp[u];
+              float2 t[Q];
+              load_t(tptr + u * TP, t);
+              const float c1 = on ? comp_s[rel * B + bb] : 0.f;
+              float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) fma2v(a2, v[NB - 1][q], t[q]);
+#pragma unroll
+              for (int q = 0; q < Q; ++q) fma2(g[NB - 1][q], c1, t[q]);
+              if (on) stg_hint(cbuf + (size_t)pos * B + bb, a2.x + a2.y, pol);
+            }
+            rp += ng; pp += ng; tptr += ng * TP;
+          }
         }
       } else {
         for (int e0 = s_lo; e0 < s_hi; e0 += 32) chunk_global(e0, min(32, s_hi - e0), v, g, true);
       }
+      if constexpr (NB > 1) {
+        for (int off = gs; off < 32; off <<= 1) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            g[NB - 1][q].x += __shfl_xor_sync(0xffffffffu, g[NB - 1][q].x, off);
+            g[NB - 1][q].y += __shfl_xor_sync(0xffffffffu, g[NB - 1][q].y, off);
+          }
+        }
+      }
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        const int b = lane + 32 * nb;
-        if (b < B) {
+        const int b = nb == 0 ? lane : bb;
+        if (b < B && (nb == 0 || qg == 0)) {
           float2 *vp = reinterpret_cast<float2 *>(vs + (size_t)b * p.vstride + jl * OUT);
 #pragma unroll
           for (int q = 0; q < Q; ++q) vp[q] = g[nb][q];
@@ -407,7 +472,9 @@ k_ident_bwd_fused(const float *__restrict__ V, const float *__restrict__ comp, c
         for (int q = 0; q < Q; ++q) g[nb][q] = make_float2(0.f, 0.f);
       for (int e0 = s_lo + warp * 32; e0 < s_hi; e0 += kCW * 32) chunk_global(e0, min(32, s_hi - e0), v, g, false);
     }
-    fence_proxy_async();   // g written with generic stores, read by the bulk store; staged data read before the next bulk load
+    // No proxy fence here: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS and would wait for the warp's
+    // scratch-row stores to be acknowledged by L2 (about a microsecond per tile).  The fence is executed by the storer / the
+    // edge loader instead, after they have acquired these arrivals and before they issue their bulk copies.
     __syncwarp();
     if (lane == 0) { mbar_arrive(&vdone[sv]); mbar_arrive(&mdone[sm]); }
   }
@@ -478,16 +545,18 @@ int launch_ident_bwd_fused(const mrgcn_graph *g, const float *V, const float *co
   const unsigned grid = (unsigned)(p.ntiles < gmax ? p.ntiles : gmax);
   const int NB = B > 32 ? 2 : 1;
   MRGCN_PROF("ident_bwd_fused");
-#define LAUNCH(OUTV, NBV)                                                                                              \
-  do {                                                                                                                 \
-    MRGCN_CUDA(cudaFuncSetAttribute(k_ident_bwd_fused<OUTV, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_ident_bwd_fused<OUTV, NBV><<<grid, kFusedThreads, smem, st>>>(V, comp, g->colptr, g->e2_dst, g->e2_rel, g->e2_val, \
-                                                                    g->e2_to_e3, gact, gW, cbuf, p);                   \
+#define LAUNCH(OUTV, NBV, NGV)                                                                                              \
+  do {                                                                                                                      \
+    MRGCN_CUDA(cudaFuncSetAttribute(k_ident_bwd_fused<OUTV, NBV, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_ident_bwd_fused<OUTV, NBV, NGV><<<grid, kFusedThreads, smem, st>>>(V, comp, g->colptr, g->e2_dst, g->e2_rel, g->e2_val, \
+                                                                         g->e2_to_e3, gact, gW, cbuf, p);                   \
   } while (0)
-#define LAUNCH_NB(OUTV) \
-  do {                  \
-    if (NB == 2) LAUNCH(OUTV, 2); \
-    else LAUNCH(OUTV, 1);         \
+#define LAUNCH_NB(OUTV)                    \
+  do {                                     \
+    if (NB == 1) LAUNCH(OUTV, 1, 1);       \
+    else if (B <= 40) LAUNCH(OUTV, 2, 4);  \
+    else if (B <= 48) LAUNCH(OUTV, 2, 2);  \
+    else LAUNCH(OUTV, 2, 1);               \
   } while (0)
   switch (out) {
     case 4: LAUNCH_NB(4); break;
