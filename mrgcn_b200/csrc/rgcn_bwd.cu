@@ -42,31 +42,38 @@ k_act_bwd(const float *__restrict__ gout, const float *__restrict__ outv, const 
           float *__restrict__ gact, float *__restrict__ colsum, int ND, int od, int relu) {
   extern __shared__ double red[];  // [kThreads]; the (small) bias sums are accumulated in double: the result is then as
                                    // close to the exact sum as the fp32 inputs allow, whatever the order
+  // block (x, y): rows [1024 x, 1024 x + 1024), columns [oc y, oc y + oc) with oc = min(od, 64): wide layers get several
+  // blocks per row range (a 14 541 x 200 layer had 15 blocks in all), every thread keeps four rows' loads in flight
   const int r0 = blockIdx.x * kColRows, r1 = min(ND, r0 + kColRows);
-  const int oc = min(od, kThreads), nslots = kThreads / oc;
+  const int oc = min(od, 64), nslots = kThreads / oc;
   const int slot = threadIdx.x / oc, ol = threadIdx.x - slot * oc;
-  for (int o0 = 0; o0 < od; o0 += oc) {
-    const int o = o0 + ol;
-    double acc = 0.0;
-    if (slot < nslots && o < od) {
-      for (int i = r0 + slot; i < r1; i += nslots) {
-        size_t x = (size_t)i * od + o;
-        float g = gout[x];
-        if (relu && !(outv[x] > 0.f)) g = 0.f;
-        if (mask) g *= mask[i];
-        gact[x] = g;
-        acc += g;
-      }
+  const int o = blockIdx.y * oc + ol;
+  const bool live = slot < nslots && o < od;
+  double acc = 0.0;
+  auto one = [&](int i, float g, float ov) {
+    if (relu && !(ov > 0.f)) g = 0.f;
+    if (mask) g *= mask[i];
+    gact[(size_t)i * od + o] = g;
+    acc += g;
+  };
+  if (live) {
+    int i = r0 + slot;
+    for (; i + 3 * nslots < r1; i += 4 * nslots) {
+      const size_t x0 = (size_t)i * od + o, st = (size_t)nslots * od;
+      const float g0 = gout[x0], g1 = gout[x0 + st], g2 = gout[x0 + 2 * st], g3 = gout[x0 + 3 * st];
+      float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+      if (relu) { v0 = outv[x0]; v1 = outv[x0 + st]; v2 = outv[x0 + 2 * st]; v3 = outv[x0 + 3 * st]; }
+      one(i, g0, v0); one(i + nslots, g1, v1); one(i + 2 * nslots, g2, v2); one(i + 3 * nslots, g3, v3);
     }
-    if (slot < nslots) red[slot * oc + ol] = acc;
-    __syncthreads();
-    for (int s = 1; s < nslots; s <<= 1) {
-      if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
-      __syncthreads();
-    }
-    if (colsum && slot == 0 && o < od) colsum[(size_t)blockIdx.x * od + o] = (float)red[ol];
+    for (; i < r1; i += nslots) one(i, gout[(size_t)i * od + o], relu ? outv[(size_t)i * od + o] : 1.f);
+  }
+  if (slot < nslots) red[slot * oc + ol] = acc;
+  __syncthreads();
+  for (int s = 1; s < nslots; s <<= 1) {
+    if (slot < nslots && (slot % (2 * s)) == 0 && slot + s < nslots) red[slot * oc + ol] += red[(slot + s) * oc + ol];
     __syncthreads();
   }
+  if (colsum && slot == 0 && o < od) colsum[(size_t)blockIdx.x * od + o] = (float)red[ol];
 }
 
 // out[s, x] = sum_c part[idx(c)*width + x] for c in [seg_ptr[s], seg_ptr[s+1]), idx = seg_idx[c] (or c) -- fixed order: 8 chunk slots stride the
@@ -696,7 +703,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
   MRGCN_REQUIRE(!a->g_bias || a->colsum_ws, MRGCN_E_BADARG, "layer_bwd: colsum_ws missing");
   if (ND > 0 && (ph & MRGCN_BWD_ACT)) {
     MRGCN_PROF("act_bwd");
-  k_act_bwd<<<nblk, kThreads, kThreads * sizeof(double), st>>>(a->gout, f.out, f.row_mask, a->gact,
+  k_act_bwd<<<dim3((unsigned)nblk, (unsigned)cdiv(out, out < 64 ? out : 64)), kThreads, kThreads * sizeof(double), st>>>(a->gout, f.out, f.row_mask, a->gact,
                                                                  a->g_bias ? a->colsum_ws : nullptr, ND, out, f.relu);
     MRGCN_LAUNCH_CHECK();
   }
@@ -898,6 +905,7 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       MRGCN_REQUIRE(gW && a->part, MRGCN_E_BADARG, "layer_bwd: g_wmix/part missing");
       static int rw_mode = -1;   // MRGCN_FEAT_RW=0 selects the thread-per-row kernel everywhere
       if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = (e && e[0] == '0') ? 0 : 1; }
+      int tile_rc = 1;
       if (gF->E > 0 && in <= 160 && out <= 16 && rw_mode == 1) {
         const int NK = (int)cdiv(in, 32);
         const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
@@ -922,6 +930,9 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
 #undef LAUNCH_NK
 #undef LAUNCH_RW
         MRGCN_LAUNCH_CHECK();
+      } else if (gF->E > 0 && (tile_rc = launch_feat_bwd_w_tile(gF, f.X, ldx, a->gact, a->part, in, out, st)) != 1) {
+        // wide outputs: register-tiled product per chunk (feat_bwd_w.cu)
+        if (tile_rc != 0) return tile_rc;
       } else if (gF->E > 0) {
         const int OC = pick_oc(out);
         int bt = (int)cdiv(in < 256 ? in : 256, 32) * 32;

@@ -98,6 +98,10 @@ int launch_tab_bwd_c(const mrgcn_graph *g, const mrgcn_tab_plan *pl, const float
 // edge; returns 1 (nothing launched) when the shape is not handled, 0 when launched, otherwise an error code
 int launch_ident_bwd_fused(const mrgcn_graph *g, const float *V, const float *comp, int B, int out, const float *gact,
                            float *gW, float *cbuf, cudaStream_t st);
+// feature-term weight gradient for wide outputs (feat_bwd_w.cu): part[c, k, o] per E3 chunk as a register-tiled product;
+// returns 1 (nothing launched) when the shape is not handled (out <= 16, out or ldx not multiples of 4, tile > 256 threads)
+int launch_feat_bwd_w_tile(const mrgcn_graph *g, const float *X, int ldx, const float *gact, float *part, int in, int out,
+                           cudaStream_t st);
 int pick_oc(int out);
 int ident_tile(int B, int out, int OP);
 struct IdentPipe;

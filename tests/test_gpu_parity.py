@@ -337,6 +337,8 @@ ORACLE_CASES = [
     (1000, 3, 6000, 45, 70, 0, False, False, False),
     (1800, 4, 12000, 145, 200, 2, True, False, False),     # YAGO3-10+ encoder shape (145 -> 200, 2 bases)
     (1600, 4, 11000, 17, 24, 3, False, False, True),
+    (1400, 4, 10000, 24, 40, 3, False, False, True),       # hidden layer wide enough for the tiled weight gradient (feat_bwd_w.cu)
+    (1300, 3, 9000, 152, 208, 0, False, False, False),     # the tile kernel's largest shape (19 x 13 threads), no bases
 ]
 
 
