@@ -248,6 +248,68 @@ k_ident_bwd_c(const float *__restrict__ V, const int32_t *__restrict__ colptr, c
   }
 }
 
+// Wide outputs (out >= 64, few bases: the link-prediction encoders, out 200 / B 2): a WARP per task of the table work plan
+// (<= 32 consecutive E2 edges of one source).  The lanes split the columns: the source's rows V[b, j, :] sit in registers
+// (NC = ceil(out / 32) floats per lane and basis, two bases at a time), every edge's gact row is read with NC coalesced
+// loads and the B dot products are finished with a fixed shuffle tree.  The lane-per-edge kernel above walks an 800-byte
+// row per lane (uncoalesced): 2.4 ms on the YAGO3-10+ shape where this one takes the time of the row reads.
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_ident_bwd_c_task(const float *__restrict__ V, const int4 *__restrict__ tasks, int n_tasks, const int32_t *__restrict__ e2_dst,
+                   const float *__restrict__ e2_val, const float *__restrict__ gact, float *__restrict__ cbuf, int64_t NS, int B,
+                   int out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int ti = blockIdx.x * wpb + (threadIdx.x >> 5); ti < n_tasks; ti += gridDim.x * wpb) {
+    const int4 tk = __ldg(tasks + ti);   // {source, first edge, number of edges, 0}
+    const int j = tk.x, e0 = tk.y, n = tk.z;
+    const int dst_l = lane < n ? e2_dst[e0 + lane] : 0;
+    const float val_l = lane < n ? e2_val[e0 + lane] : 0.f;
+    for (int b0 = 0; b0 < B; b0 += 2) {
+      float v0[NC], v1[NC];
+      const bool two = b0 + 1 < B;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int o = lane + 32 * c;
+        v0[c] = o < out ? __ldg(V + ((size_t)b0 * NS + j) * out + o) : 0.f;
+        v1[c] = (two && o < out) ? __ldg(V + ((size_t)(b0 + 1) * NS + j) * out + o) : 0.f;
+      }
+      for (int i = 0; i < n; i += 2) {
+        // two edges per trip: their row loads are in flight together
+        const int d0 = __shfl_sync(0xffffffffu, dst_l, i), d1 = __shfl_sync(0xffffffffu, dst_l, min(i + 1, n - 1));
+        const float w0 = __shfl_sync(0xffffffffu, val_l, i), w1 = __shfl_sync(0xffffffffu, val_l, min(i + 1, n - 1));
+        float t0[NC], t1[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int o = lane + 32 * c;
+          t0[c] = o < out ? __ldg(gact + (size_t)d0 * out + o) : 0.f;
+          t1[c] = o < out ? __ldg(gact + (size_t)d1 * out + o) : 0.f;
+        }
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;   // a[edge][basis]
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          a00 = fmaf(v0[c], t0[c], a00); a01 = fmaf(v1[c], t0[c], a01);
+          a10 = fmaf(v0[c], t1[c], a10); a11 = fmaf(v1[c], t1[c], a11);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          a00 += __shfl_xor_sync(0xffffffffu, a00, off); a01 += __shfl_xor_sync(0xffffffffu, a01, off);
+          a10 += __shfl_xor_sync(0xffffffffu, a10, off); a11 += __shfl_xor_sync(0xffffffffu, a11, off);
+        }
+        if (lane == 0) {
+          float *c0 = cbuf + (size_t)(e0 + i) * B + b0;
+          c0[0] = w0 * a00;
+          if (two) c0[1] = w0 * a01;
+          if (i + 1 < n) {
+            c0[B] = w1 * a10;
+            if (two) c0[B + 1] = w1 * a11;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- identity term, B > 0, basis gradient: g_weight_I[b, j, o] = sum_{e: src=j} comp[r_e,b] * t_e[o] ----
 // A CTA walks tiles of TJ sources (TJ*out <= 256).  Per tile: (1) every thread stages t_e = val_e*gact[dst_e,:]
 // of one edge into shared memory (all gathers independent -> deep memory-level parallelism), (2) one thread per
@@ -829,6 +891,25 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
           IdentPipe p;
           if (fused) {
             // scratch rows already written, in E3 order
+          } else if (f.plan && f.plan->n_tasks > 0 && f.plan->lt <= 32 && out >= 64 && out <= 256 && B <= 8) {
+            const int NC = (int)cdiv(out, 32);
+            const int64_t blocks = cdiv(f.plan->n_tasks, 8);
+            const unsigned gridt = (unsigned)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs);
+            const int4 *tk = reinterpret_cast<const int4 *>(f.plan->tasks4);
+            MRGCN_PROF("ident_bwd_c");
+#define LAUNCH_T(NCV) \
+  k_ident_bwd_c_task<NCV><<<gridt, 256, 0, st>>>(f.weight_I, tk, f.plan->n_tasks, gI->e2_dst, gI->e2_val, a->gact, a->cbuf, NS, B, out)
+            switch (NC) {
+              case 2: LAUNCH_T(2); break;
+              case 3: LAUNCH_T(3); break;
+              case 4: LAUNCH_T(4); break;
+              case 5: LAUNCH_T(5); break;
+              case 6: LAUNCH_T(6); break;
+              case 7: LAUNCH_T(7); break;
+              default: LAUNCH_T(8); break;
+            }
+#undef LAUNCH_T
+            MRGCN_LAUNCH_CHECK();
           } else if (ident_pipe_config(p, NS, B, out, 0)) {
             const int VW = (out % 4 == 0) ? 4 : (out % 2 == 0) ? 2 : 1;
             smem = 16 * ((2 * p.S * 8 + 15) / 16) + (size_t)p.S * p.stage_bytes;
