@@ -240,7 +240,8 @@ int mrgcn_distmult_fwd(const int64_t *s, const int64_t *p, const int64_t *o, int
                        const float *E, const float *Rel, int32_t h, float *score,
                        mrgcn_stream_t stream);
 /* Backward: gE [N,h] and gRel [NR,h] are fully written (rows without triples = 0).
- * ws: int32 workspace of mrgcn_distmult_bwd_ws_elems(n) elements. */
+ * ws: int32 workspace of mrgcn_distmult_bwd_ws_elems(n) elements (incidence lists + the temporary storage of the
+ * library radix sort that orders them: nothing is allocated inside the call). */
 int64_t mrgcn_distmult_bwd_ws_elems(int64_t n);
 int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n,
                        const float *gscore, const float *E, const float *Rel,

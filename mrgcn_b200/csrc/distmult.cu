@@ -87,14 +87,24 @@ k_distmult_bwd_rels(const int32_t *__restrict__ keys, const int32_t *__restrict_
   }
 }
 
-static int sort_i32(int32_t *kin, int32_t *kout, int32_t *vin, int32_t *vout, int64_t m, cudaStream_t st) {
+// temporary storage of the radix sort of m (key, value) pairs: part of the caller's workspace (no allocation in here)
+static size_t sort_temp_bytes(int64_t m) {
+  size_t bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                                  (const int32_t *)nullptr, (int32_t *)nullptr, (int)m, 0, 32, (cudaStream_t)0);
+  if (e != cudaSuccess) {   // no device (host-only tests): a bound that only sizes a buffer nobody will use
+    (void)cudaGetLastError();
+    bytes = (size_t)(1 << 20) + 64 * (size_t)m;
+  }
+  return (bytes + 255) & ~(size_t)255;
+}
+static int sort_i32(int32_t *kin, int32_t *kout, int32_t *vin, int32_t *vout, int64_t m, void *tmp, size_t tmp_bytes,
+                    cudaStream_t st) {
   size_t bytes = 0;
   MRGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)m, 0, 32, st));
-  void *tmp = nullptr;
-  MRGCN_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)m, 0, 32, st);
-  cudaFreeAsync(tmp, st);
-  MRGCN_CUDA(e);
+  MRGCN_REQUIRE(bytes <= tmp_bytes, MRGCN_E_BADARG, "distmult_bwd: workspace too small for the sort (%zu > %zu bytes)", bytes,
+                tmp_bytes);
+  MRGCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)m, 0, 32, st));
   count_launch(3);
   return 0;
 }
@@ -115,7 +125,12 @@ extern "C" int mrgcn_distmult_fwd(const int64_t *s, const int64_t *p, const int6
   return 0;
 }
 
-extern "C" int64_t mrgcn_distmult_bwd_ws_elems(int64_t n) { return 12 * (n > 0 ? n : 1); }
+// 12 n index words (incidence lists and their sorted copies), padded to 256 bytes, + the sort's temporary storage
+static int64_t ws_index_words(int64_t n) { return ((12 * n + 63) / 64) * 64; }
+extern "C" int64_t mrgcn_distmult_bwd_ws_elems(int64_t n) {
+  n = n > 0 ? n : 1;
+  return ws_index_words(n) + (int64_t)(sort_temp_bytes(2 * n) / 4);
+}
 
 extern "C" int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int64_t *o, int64_t n, const float *gscore,
                                   const float *E, const float *Rel, int64_t N, int64_t NR, int32_t h, float *gE,
@@ -128,17 +143,19 @@ extern "C" int mrgcn_distmult_bwd(const int64_t *s, const int64_t *p, const int6
   if (n == 0) return 0;
   int32_t *nk = ws, *nko = ws + 2 * n, *nv = ws + 4 * n, *nvo = ws + 6 * n;
   int32_t *pk = ws + 8 * n, *pko = ws + 9 * n, *pv = ws + 10 * n, *pvo = ws + 11 * n;
+  void *tmp = ws + ws_index_words(n);
+  const size_t tmp_bytes = sort_temp_bytes(2 * n);
   k_incidence<<<(unsigned)cdiv(n, kThreads), kThreads, 0, st>>>(s, p, o, n, nk, nv, pk, pv);
   MRGCN_LAUNCH_CHECK();
   if (gE) {
-    if (int rc = sort_i32(nk, nko, nv, nvo, 2 * n, st)) return rc;
+    if (int rc = sort_i32(nk, nko, nv, nvo, 2 * n, tmp, tmp_bytes, st)) return rc;
     MRGCN_PROF("distmult_bwd_nodes");
   k_distmult_bwd_nodes<<<(unsigned)cdiv(2 * n * 32, kThreads), kThreads, 0, st>>>(nko, nvo, 2 * n, n, s, p, o, gscore, E,
                                                                                     Rel, h, gE);
     MRGCN_LAUNCH_CHECK();
   }
   if (gRel) {
-    if (int rc = sort_i32(pk, pko, pv, pvo, n, st)) return rc;
+    if (int rc = sort_i32(pk, pko, pv, pvo, n, tmp, tmp_bytes, st)) return rc;
     MRGCN_PROF("distmult_bwd_rels");
   k_distmult_bwd_rels<<<(unsigned)cdiv(n * 32, kThreads), kThreads, 0, st>>>(pko, pvo, n, s, o, gscore, E, h, gRel);
     MRGCN_LAUNCH_CHECK();
