@@ -54,15 +54,38 @@ k_distmult_bwd_nodes(const int32_t *__restrict__ keys, const int32_t *__restrict
   if (q > 0 && keys[q - 1] == node) return;
   int64_t end = q + 1;
   while (end < m && keys[end] == node) ++end;
-  for (int k = lane; k < h; k += 32) {
-    float acc = 0.f;
-    for (int64_t x = q; x < end; ++x) {
-      const int v = vals[x];
-      const int64_t t = v < n ? v : v - n;
-      const int64_t other = v < n ? o[t] : s[t];
-      acc = fmaf(g[t], Rel[(size_t)p[t] * h + k] * E[(size_t)other * h + k], acc);
+  // the run's entries in order (fixed order => reproducible); per entry the index chain vals -> (p, other, g) is followed once
+  // for all columns (KB x 32 of them in registers), two entries per trip so that their row loads are in flight together
+  constexpr int KB = 8;
+  for (int k0 = 0; k0 < h; k0 += 32 * KB) {
+    float acc[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c) acc[c] = 0.f;
+    for (int64_t x = q; x < end; x += 2) {
+      const bool two = x + 1 < end;
+      const int v0 = vals[x], v1 = two ? vals[x + 1] : vals[x];
+      const int64_t t0 = v0 < n ? v0 : v0 - n, t1 = v1 < n ? v1 : v1 - n;
+      const float *r0 = Rel + (size_t)p[t0] * h, *r1 = Rel + (size_t)p[t1] * h;
+      const float *e0 = E + (size_t)(v0 < n ? o[t0] : s[t0]) * h, *e1 = E + (size_t)(v1 < n ? o[t1] : s[t1]) * h;
+      const float g0 = g[t0], g1 = g[t1];
+      float a[KB], b[KB];
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        const int k = k0 + lane + 32 * c;
+        a[c] = k < h ? r0[k] * e0[k] : 0.f;
+        b[c] = (two && k < h) ? r1[k] * e1[k] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        acc[c] = fmaf(g0, a[c], acc[c]);
+        if (two) acc[c] = fmaf(g1, b[c], acc[c]);
+      }
     }
-    gE[(size_t)node * h + k] = acc;
+#pragma unroll
+    for (int c = 0; c < KB; ++c) {
+      const int k = k0 + lane + 32 * c;
+      if (k < h) gE[(size_t)node * h + k] = acc[c];
+    }
   }
 }
 
@@ -77,13 +100,35 @@ k_distmult_bwd_rels(const int32_t *__restrict__ keys, const int32_t *__restrict_
   if (q > 0 && keys[q - 1] == rel) return;
   int64_t end = q + 1;
   while (end < n && keys[end] == rel) ++end;
-  for (int k = lane; k < h; k += 32) {
-    float acc = 0.f;
-    for (int64_t x = q; x < end; ++x) {
-      const int64_t t = vals[x];
-      acc = fmaf(g[t], E[(size_t)s[t] * h + k] * E[(size_t)o[t] * h + k], acc);
+  constexpr int KB = 8;   // as above: a popular relation holds a fifth of the batch, its run was one long dependent chain
+  for (int k0 = 0; k0 < h; k0 += 32 * KB) {
+    float acc[KB];
+#pragma unroll
+    for (int c = 0; c < KB; ++c) acc[c] = 0.f;
+    for (int64_t x = q; x < end; x += 2) {
+      const bool two = x + 1 < end;
+      const int64_t t0 = vals[x], t1 = two ? vals[x + 1] : vals[x];
+      const float *s0 = E + (size_t)s[t0] * h, *o0 = E + (size_t)o[t0] * h;
+      const float *s1 = E + (size_t)s[t1] * h, *o1 = E + (size_t)o[t1] * h;
+      const float g0 = g[t0], g1 = g[t1];
+      float a[KB], b[KB];
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        const int k = k0 + lane + 32 * c;
+        a[c] = k < h ? s0[k] * o0[k] : 0.f;
+        b[c] = (two && k < h) ? s1[k] * o1[k] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < KB; ++c) {
+        acc[c] = fmaf(g0, a[c], acc[c]);
+        if (two) acc[c] = fmaf(g1, b[c], acc[c]);
+      }
     }
-    gRel[(size_t)rel * h + k] = acc;
+#pragma unroll
+    for (int c = 0; c < KB; ++c) {
+      const int k = k0 + lane + 32 * c;
+      if (k < h) gRel[(size_t)rel * h + k] = acc[c];
+    }
   }
 }
 
