@@ -617,7 +617,7 @@ __global__ void k_feat_bwd_w(const float *__restrict__ X, const float *__restric
 // sums are added in warp order.  ~3x fewer shared-pipe wavefronts than k_feat_bwd_w (ncu r01_feat: that one is bound by
 // the L1/shared data pipe).
 template <int NK, int OC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 k_feat_bwd_w_rw(const float *__restrict__ X, const float *__restrict__ gact, const int32_t *__restrict__ chunk_ptr,
                 const int32_t *__restrict__ e3_src, const int32_t *__restrict__ e3_dst,
                 const float *__restrict__ e3_val, float *__restrict__ part, int in, int out, int ldx) {
