@@ -96,3 +96,14 @@ def test_model_state_dict_keys_match_reference_layout():
     sd = m.state_dict()
     assert tuple(sd["rgcn.layers.layer_0.weight_I"].shape) == (3 * 61, 6) and tuple(sd["rgcn.relations"].shape) == (9, 3)
     assert m.devices["relational"].type in ("cuda", "cpu") and m.gate_map == {"xsd_numeric_0": 0}
+
+
+def test_distmult_workspace_covers_index_lists_and_sort_storage():
+    """mrgcn_distmult_bwd_ws_elems(n): 12 n index words + the radix sort's temporary storage (a size query: no GPU needed);
+    nothing is allocated inside mrgcn_distmult_bwd (include/mrgcn_b200.h)."""
+    from mrgcn_b200 import _native as nv
+    lib = nv.lib()
+    for n in (1, 600, 100000):
+        w = int(lib.mrgcn_distmult_bwd_ws_elems(n))
+        assert w >= 12 * n + 64, (n, w)
+    assert int(lib.mrgcn_distmult_bwd_ws_elems(0)) == int(lib.mrgcn_distmult_bwd_ws_elems(1))
