@@ -450,13 +450,14 @@ k_ident_bwd_w_long(const float *__restrict__ comp, HubSegs h, const int32_t *__r
     for (int c_lo = s_lo; c_lo < s_hi; c_lo += EL) {
       const int n = min(EL, s_hi - c_lo);
       __syncthreads();
-      for (int el = tid; el < n; el += kHubThreads) {
+      // all threads stage the chunk's t_e rows, coalesced along the row (a thread per edge walked a whole row alone: 200
+      // dependent loads per thread on the link-prediction encoders)
+      for (int x = tid; x < n * out; x += kHubThreads) {
+        const int el = x / out, q = x - el * out;
         const int e = c_lo + el;
-        const float v = e2_val[e];
-        const float *gp = gact + (size_t)e2_dst[e] * out;
-        Rs[el] = e2_rel[e] * B;
-        for (int q = 0; q < out; ++q) Ts[el * out + q] = v * gp[q];
+        Ts[x] = e2_val[e] * gact[(size_t)e2_dst[e] * out + q];
       }
+      for (int el = tid; el < n; el += kHubThreads) Rs[el] = e2_rel[c_lo + el] * B;
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < PP; ++q) {
