@@ -352,6 +352,47 @@ __global__ void __launch_bounds__(kThreads) k_agg_fwd(AggArgs a) {
   }
 }
 
+// wide rows (32 <= out <= 256, messages only): a warp per destination row keeps all NC = ceil(out/32) column chunks of the
+// row in registers and walks the row's edges ONCE, two message rows in flight (k_agg_fwd re-walks the edge list and its
+// permutation once per 32 columns).  Same summation order per element as k_agg_fwd: identical results.
+template <int NC>
+__global__ void __launch_bounds__(kThreads) k_agg_fwd_wide(AggArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5);
+  if (i >= a.ND) return;
+  if (a.thresh > 0 && row_degree(a, i) > a.thresh) return;
+  const int od = a.odim, ms = a.ms;
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+  auto walk = [&](const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi) {
+    int e = lo;
+    for (; e + 1 < hi; e += 2) {
+      const float *r0 = msg + (size_t)perm[e] * ms + lane, *r1 = msg + (size_t)perm[e + 1] * ms + lane;
+      float v0[NC], v1[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const bool in = lane + 32 * c < od;
+        v0[c] = in ? r0[32 * c] : 0.f;
+        v1[c] = in ? r1[32 * c] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { acc[c] += v0[c]; acc[c] += v1[c]; }
+    }
+    if (e < hi) {
+      const float *r0 = msg + (size_t)perm[e] * ms + lane;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (lane + 32 * c < od) acc[c] += r0[32 * c];
+    }
+  };
+  if (a.rowptr && a.msgI) walk(a.msgI, a.pI, a.rowptr[i], a.rowptr[i + 1]);
+  if (a.msgF) walk(a.msgF, a.pF, a.rowptrF[i], a.rowptrF[i + 1]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if (lane + 32 * c < od) agg_store(a, i, lane + 32 * c, acc[c]);
+}
+
 // short rows, vector variant: MS/4 lanes per row, each lane owns 4 consecutive outputs and gathers 16-byte pieces of the
 // (64-byte aligned) message rows; four gathers in flight; fixed order.
 __device__ __forceinline__ void gather_sum4(const float *__restrict__ msg, const int32_t *__restrict__ perm, int lo, int hi,
@@ -598,6 +639,18 @@ int launch_agg(const AggArgs &g, const HubSegs &h, cudaStream_t st, const char *
     const int rows_per_warp = 32 / (g.ms >> 2);
     unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
     k_agg_fwd_v4<<<grid, kThreads, 0, st>>>(g);
+  } else if (g.odim >= 32 && g.odim <= 256 && !g.Wd && (g.msgI || g.msgF)) {
+    unsigned grid = (unsigned)cdiv((int64_t)g.ND * 32, kThreads);
+    switch ((g.odim + 31) / 32) {
+      case 1: k_agg_fwd_wide<1><<<grid, kThreads, 0, st>>>(g); break;
+      case 2: k_agg_fwd_wide<2><<<grid, kThreads, 0, st>>>(g); break;
+      case 3: k_agg_fwd_wide<3><<<grid, kThreads, 0, st>>>(g); break;
+      case 4: k_agg_fwd_wide<4><<<grid, kThreads, 0, st>>>(g); break;
+      case 5: k_agg_fwd_wide<5><<<grid, kThreads, 0, st>>>(g); break;
+      case 6: k_agg_fwd_wide<6><<<grid, kThreads, 0, st>>>(g); break;
+      case 7: k_agg_fwd_wide<7><<<grid, kThreads, 0, st>>>(g); break;
+      default: k_agg_fwd_wide<8><<<grid, kThreads, 0, st>>>(g); break;
+    }
   } else {
     const int rows_per_warp = g.odim >= 32 ? 1 : 32 / g.odim;
     unsigned grid = (unsigned)cdiv(cdiv(g.ND, rows_per_warp) * 32, kThreads);
