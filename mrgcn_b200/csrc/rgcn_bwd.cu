@@ -707,6 +707,61 @@ k_feat_bwd_w_rw(const float *__restrict__ X, const float *__restrict__ gact, con
   }
 }
 
+// Tiny layers (in * ceil(out/4) <= 32: AM hidden layer 10 -> 11, AIFB 16 -> 4): lane = (k, group of 4 outputs), so that
+// (nearly) all lanes multiply - in k_feat_bwd_w_rw only the first `in` lanes of a warp own rows of g_W (10 of 32 on AM) and
+// every one of them reads the whole t_e row.  Same edge order per accumulator and same warp order: identical results.
+template <int OC>
+__global__ void __launch_bounds__(128)
+k_feat_bwd_w_small(const float *__restrict__ X, const float *__restrict__ gact, const int32_t *__restrict__ chunk_ptr,
+                   const int32_t *__restrict__ e3_src, const int32_t *__restrict__ e3_dst, const float *__restrict__ e3_val,
+                   float *__restrict__ part, int in, int out, int ldx) {
+  constexpr int NW = 4, NOC = OC / 4;
+  __shared__ __align__(16) float Ts[NW][32][OC];
+  __shared__ int Js[NW][32];
+  __shared__ __align__(16) float red[NW - 1][32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = lane / NOC, oc = lane - k * NOC;
+  const bool act = k < in;
+  const int c = blockIdx.x;
+  const int e_lo = chunk_ptr[c], e_hi = chunk_ptr[c + 1];
+  float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+  for (int eb = e_lo + warp * 32; eb < e_hi; eb += NW * 32) {
+    const int nb = min(32, e_hi - eb);
+    __syncwarp();
+    {
+      const int e = eb + lane;
+      const bool live = lane < nb;
+      const float v = live ? e3_val[e] : 0.f;
+      const float *gp = gact + (size_t)(live ? e3_dst[e] : 0) * out;
+      Js[warp][lane] = live ? e3_src[e] : 0;
+#pragma unroll
+      for (int o = 0; o < OC; ++o) Ts[warp][lane][o] = (live && o < out) ? v * gp[o] : 0.f;
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {  // padded entries have t = 0 and read row 0 (valid memory)
+      const float x = act ? __ldg(X + (size_t)Js[warp][i] * ldx + k) : 0.f;
+      const float4 t4 = *reinterpret_cast<const float4 *>(&Ts[warp][i][4 * oc]);
+      fma2(a0, x, make_float2(t4.x, t4.y));
+      fma2(a1, x, make_float2(t4.z, t4.w));
+    }
+  }
+  if (warp > 0) *reinterpret_cast<float4 *>(red[warp - 1][lane]) = make_float4(a0.x, a0.y, a1.x, a1.y);
+  __syncthreads();
+  if (warp == 0 && act) {
+    float r[4] = {a0.x, a0.y, a1.x, a1.y};
+#pragma unroll
+    for (int w2 = 0; w2 < NW - 1; ++w2) {
+      const float4 q = *reinterpret_cast<const float4 *>(red[w2][lane]);
+      r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
+    }
+    float *pp = part + ((size_t)c * in + k) * out + 4 * oc;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * oc + u < out) pp[u] = r[u];
+  }
+}
+
 // ---- basis gradients of the feature weights (graph.py:83-85 backwards).  Tiny. ---------------------
 __global__ void k_basis_mix_bwd_v(const float *__restrict__ comp, const float *__restrict__ gW, float *__restrict__ gV,
                                   int R, int B, int IO) {
@@ -988,7 +1043,19 @@ extern "C" int mrgcn_rgcn_layer_bwd(const mrgcn_layer_bwd_args *a, mrgcn_stream_
       static int rw_mode = -1;   // MRGCN_FEAT_RW=0 selects the thread-per-row kernel everywhere
       if (rw_mode < 0) { const char *e = getenv("MRGCN_FEAT_RW"); rw_mode = (e && e[0] == '0') ? 0 : 1; }
       int tile_rc = 1;
-      if (gF->E > 0 && in <= 160 && out <= 16 && rw_mode == 1) {
+      if (gF->E > 0 && out <= 12 && in * (((out + 3) / 4)) <= 32 && rw_mode == 1) {
+        const int OCS = ((out + 3) / 4) * 4;
+        MRGCN_PROF("feat_bwd_w");
+#define LAUNCH_S(OCV) \
+  k_feat_bwd_w_small<OCV><<<(unsigned)gF->n_chunks, 128, 0, st>>>(f.X, a->gact, gF->chunk_ptr, gF->e3_src, gF->e3_dst, gF->e3_val, a->part, in, out, ldx)
+        switch (OCS) {
+          case 4: LAUNCH_S(4); break;
+          case 8: LAUNCH_S(8); break;
+          default: LAUNCH_S(12); break;
+        }
+#undef LAUNCH_S
+        MRGCN_LAUNCH_CHECK();
+      } else if (gF->E > 0 && in <= 160 && out <= 16 && rw_mode == 1) {
         const int NK = (int)cdiv(in, 32);
         const int OCR = out <= 4 ? 4 : out <= 8 ? 8 : out <= 10 ? 10 : out <= 12 ? 12 : 16;
         MRGCN_PROF("feat_bwd_w");
